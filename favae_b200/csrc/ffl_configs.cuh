@@ -1,0 +1,14 @@
+// Kernel configurations of the fused spectrum-loss kernel, shared by the CUDA build
+// and the host emulation (tests/emul/ffl_emul.cpp).
+#pragma once
+#include "ffl_core.cuh"
+
+namespace favae {
+//                      N    C  MPC  THREADS
+using FflCfg8   = FflCfg<8,   1, 32, 128>;
+using FflCfg16  = FflCfg<16,  1, 16, 128>;
+using FflCfg32  = FflCfg<32,  1, 4,  256>;
+using FflCfg64  = FflCfg<64,  1, 1,  256>;
+using FflCfg128 = FflCfg<128, 1, 1,  512>;
+using FflCfg256 = FflCfg<256, 2, 1,  512>;
+}  // namespace favae

@@ -1,0 +1,249 @@
+// Fused spectrum-loss core: one real 2-D FFT of (pred - target), dynamic spectrum
+// weight, weighted energy, and the weighted inverse transform (= the gradient).
+//
+// Replaces focal_frequency_loss.FocalFrequencyLoss.forward / tensor2freq /
+// loss_formulation (pip focal-frequency-loss==0.3.0, called from
+// /root/reference/losses/vqgan_losses.py:14,25-26,45-46) and its autograd backward.
+//
+// The same source is compiled by nvcc for sm_100a and by g++ for the host emulation
+// used in tests/test_ffl_emulation.py (thread loops instead of threads), so every
+// cross-thread exchange happens at an explicit FAVAE_SYNC point.
+//
+// Math.  d = pred - target (real, N x N, N a power of two).
+//   * rows r' and r'+N/2 are packed as one complex row z = d[r'] + i d[r'+N/2]
+//   * row FFT (length N) of the N/2 packed rows -> Z[r'][v]  (stored S[v][r'])
+//   * column group v in [1, N/2): separates Dr[r][v] from Z[.][v], Z[.][N-v] on load,
+//     FFT over rows -> T[v][u] = unnormalised spectrum D[u][v]
+//     column group 0 packs the two real columns v=0 and v=N/2 as one complex column
+//   * stats: f(A) with A = |D|/N; sum f(A) A^2 (mirror half counted via weight 2), max f(A)
+//   * weight, inverse column FFT, re-pack, inverse row FFT -> grad rows r', r'+N/2
+//
+// 1-D FFT of length N = R1*R2 on TG = R2 threads, R1 values per thread:
+//   forward : x[R2*e + t] --FFT_R1--> *W_N^(t*k1) --exchange--> FFT_R2 --> X[t + R2*m + R1*k2]
+//             (register e = m*R2 + k2)
+//   inverse : the same pipeline run backwards, so the inverse consumes the forward's
+//             output layout and produces its input layout: every phase reads and writes
+//             exactly the addresses it touched on the way in.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FAVAE_HD __host__ __device__ __forceinline__
+#else
+#define FAVAE_HD inline
+#ifndef FAVAE_HOST_FLOAT2
+#define FAVAE_HOST_FLOAT2
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+#endif
+#endif
+
+namespace favae {
+
+// ----------------------------------------------------------------------------------
+// complex helpers
+// ----------------------------------------------------------------------------------
+FAVAE_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+FAVAE_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+FAVAE_HD float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// multiply by -i (DIR=-1, forward) or +i (DIR=+1, inverse)
+template <int DIR> FAVAE_HD float2 crot(float2 a) {
+  return DIR < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
+}
+
+// twiddle e^{DIR * 2*pi*i * j/16}, j = 0..7, as compile-time constants
+template <int J, int DIR> FAVAE_HD float2 ctw16(float2 a) {
+  constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
+  if constexpr (J == 0) return a;
+  else if constexpr (J == 4) return crot<DIR>(a);
+  else {
+    constexpr float c = (J == 1) ? C1 : (J == 2) ? R2 : (J == 3) ? S1 : (J == 5) ? -S1 : (J == 6) ? -R2 : -C1;
+    constexpr float s0 = (J == 1) ? S1 : (J == 2) ? R2 : (J == 3) ? C1 : (J == 5) ? C1 : (J == 6) ? R2 : S1;
+    constexpr float s = DIR < 0 ? -s0 : s0;
+    return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+  }
+}
+
+// ----------------------------------------------------------------------------------
+// in-register FFT of R in {1,2,4,8,16} values, natural order in and out
+// ----------------------------------------------------------------------------------
+template <int R, int DIR> struct RegFFT;
+
+template <int DIR> struct RegFFT<1, DIR> {
+  static FAVAE_HD void run(float2 (&)[1]) {}
+};
+template <int DIR> struct RegFFT<2, DIR> {
+  static FAVAE_HD void run(float2 (&v)[2]) {
+    float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b); v[1] = csub(a, b);
+  }
+};
+
+template <int R, int DIR, int K> struct Combine {
+  static FAVAE_HD void run(float2 (&v)[R], const float2 (&e)[R / 2], const float2 (&o)[R / 2]) {
+    float2 t = ctw16<K * (16 / R), DIR>(o[K]);
+    v[K] = cadd(e[K], t);
+    v[K + R / 2] = csub(e[K], t);
+    if constexpr (K + 1 < R / 2) Combine<R, DIR, K + 1>::run(v, e, o);
+  }
+};
+
+template <int R, int DIR> struct RegFFT {
+  static FAVAE_HD void run(float2 (&v)[R]) {
+    float2 e[R / 2], o[R / 2];
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k) { e[k] = v[2 * k]; o[k] = v[2 * k + 1]; }
+    RegFFT<R / 2, DIR>::run(e);
+    RegFFT<R / 2, DIR>::run(o);
+    Combine<R, DIR, 0>::run(v, e, o);
+  }
+};
+
+// ----------------------------------------------------------------------------------
+// geometry
+// ----------------------------------------------------------------------------------
+template <int N> struct FftGeom;
+template <> struct FftGeom<8>   { static constexpr int R1 = 8,  R2 = 1; };
+template <> struct FftGeom<16>  { static constexpr int R1 = 16, R2 = 1; };
+template <> struct FftGeom<32>  { static constexpr int R1 = 8,  R2 = 4; };
+template <> struct FftGeom<64>  { static constexpr int R1 = 8,  R2 = 8; };
+template <> struct FftGeom<128> { static constexpr int R1 = 16, R2 = 8; };
+template <> struct FftGeom<256> { static constexpr int R1 = 16, R2 = 16; };
+
+// N: map side; C: CTAs per cluster sharing one map; MPC: maps per CTA (C==1 only)
+template <int N_, int C_, int MPC_, int THREADS_> struct FflCfg {
+  static constexpr int N = N_, C = C_, MPC = MPC_, THREADS = THREADS_;
+  static constexpr int R1 = FftGeom<N>::R1, R2 = FftGeom<N>::R2;
+  static constexpr int TG = R2;                    // threads per 1-D FFT
+  static constexpr int NG = THREADS / TG;          // 1-D FFTs in flight per CTA
+  static constexpr int HALF = N / 2;
+  static constexpr int ITEMS = MPC * HALF / C;     // row pairs (= column groups) per CTA
+  static constexpr int PASSES = ITEMS / NG;
+  static constexpr int COLSTRIDE = HALF + 1;       // float2 per S column (padded)
+  static constexpr int S_FLOAT2 = MPC * (N / C) * COLSTRIDE;
+  static constexpr int STG_STRIDE = R2 + 1;
+  static constexpr int STG_FLOAT2 = (R2 > 1) ? NG * R1 * STG_STRIDE : 1;
+  static constexpr int PO_IN = R1 / 2;                         // register offset of n + N/2
+  static constexpr int PO_OUT = (R2 >= 2) ? R2 / 2 : R1 / 2;   // register offset of k + N/2
+  static constexpr int TMAP = HALF * TG / C;       // threads of one CTA working on one map
+  static_assert(ITEMS % NG == 0 && PASSES >= 1, "items must tile the thread groups");
+  static_assert(C == 1 || MPC == 1, "clusters hold a single map");
+  static_assert(32 % TG == 0, "a 1-D FFT group must sit inside a warp");
+  static constexpr size_t SMEM_BYTES =
+      sizeof(float2) * (size_t)(S_FLOAT2 + STG_FLOAT2) + sizeof(float) * (size_t)(4 * THREADS + 8 * MPC + 8 * C);
+};
+
+// per-thread registers that live across FAVAE_SYNC points
+template <class Cfg> struct ThreadRegs {
+  float2 v[Cfg::R1];        // FFT payload
+  float2 tw[Cfg::R1];       // W_N^(t*k1), forward sign
+  float sum, mx;            // running stats
+};
+
+struct FflParams {
+  const float* pred;        // maps * N * N
+  const float* target;
+  float* grad_pred;         // nullable
+  float* grad_target;       // nullable (written as -grad)
+  float* map_loss;          // maps: sum_{u,v} w A^2 per map (unscaled by loss_weight / numel)
+  long long maps;
+  float grad_scale;         // 2*loss_weight/numel / (N*N)
+  float alpha;
+  int log_matrix;
+};
+
+// out-layout / in-layout index of register e of lane t
+template <class Cfg> FAVAE_HD int idx_in(int t, int e) { return Cfg::R2 * e + t; }
+template <class Cfg> FAVAE_HD int idx_out(int t, int e) {
+  return t + Cfg::R2 * (e / Cfg::R2) + Cfg::R1 * (e % Cfg::R2);
+}
+
+// S addressing: column w in [0,N) of the map -> (owner CTA, float2 offset of row 0)
+template <class Cfg> FAVAE_HD void s_locate(int w, int slot_map, int& owner, int& off) {
+  constexpr int N = Cfg::N, HALF = Cfg::HALF, GPC = HALF / Cfg::C;   // groups per CTA
+  int group, sub;
+  if (w == 0) { group = 0; sub = 0; }
+  else if (w == HALF) { group = 0; sub = 1; }
+  else if (w < HALF) { group = w; sub = 0; }
+  else { group = N - w; sub = 1; }
+  owner = group / GPC;
+  off = ((slot_map * GPC + (group % GPC)) * 2 + sub) * Cfg::COLSTRIDE;
+}
+
+// f(A) from A^2 (already ortho-normalised)
+FAVAE_HD float spectrum_f(float a2, float alpha, int log_matrix) {
+  float f;
+  if (alpha == 1.0f) f = sqrtf(a2);
+  else if (alpha == 2.0f) f = a2;
+  else f = powf(sqrtf(a2), alpha);
+  if (log_matrix) f = logf(f + 1.0f);
+  return f;
+}
+
+// weight = clamp(nan_to_0(f / fmax), 0, 1)
+FAVAE_HD float spectrum_w(float f, float fmax) {
+  float w = f / fmax;
+  if (!(w == w)) w = 0.0f;
+  return fminf(fmaxf(w, 0.0f), 1.0f);
+}
+
+// ----------------------------------------------------------------------------------
+// 1-D FFT stages.  stg points at this group's staging area (R1 * STG_STRIDE float2).
+// ----------------------------------------------------------------------------------
+template <class Cfg> FAVAE_HD void fwd_stage1(ThreadRegs<Cfg>& r, int t, float2* stg) {
+  RegFFT<Cfg::R1, -1>::run(r.v);
+  if constexpr (Cfg::R2 > 1) {
+#pragma unroll
+    for (int k1 = 0; k1 < Cfg::R1; ++k1) {
+      float2 y = (k1 == 0) ? r.v[0] : cmul(r.v[k1], r.tw[k1]);
+      stg[k1 * Cfg::STG_STRIDE + t] = y;
+    }
+  }
+}
+template <class Cfg> FAVAE_HD void fwd_stage2(ThreadRegs<Cfg>& r, int t, const float2* stg) {
+  if constexpr (Cfg::R2 > 1) {
+    constexpr int M = Cfg::R1 / Cfg::R2;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      float2 b[Cfg::R2];
+      const int k1 = t + Cfg::R2 * m;
+#pragma unroll
+      for (int n2 = 0; n2 < Cfg::R2; ++n2) b[n2] = stg[k1 * Cfg::STG_STRIDE + n2];
+      RegFFT<Cfg::R2, -1>::run(b);
+#pragma unroll
+      for (int k2 = 0; k2 < Cfg::R2; ++k2) r.v[m * Cfg::R2 + k2] = b[k2];
+    }
+  }
+}
+// inverse: consumes out-layout registers, produces in-layout registers (unnormalised)
+template <class Cfg> FAVAE_HD void inv_stage1(ThreadRegs<Cfg>& r, int t, float2* stg) {
+  if constexpr (Cfg::R2 > 1) {
+    constexpr int M = Cfg::R1 / Cfg::R2;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      float2 b[Cfg::R2];
+      const int k1 = t + Cfg::R2 * m;
+#pragma unroll
+      for (int k2 = 0; k2 < Cfg::R2; ++k2) b[k2] = r.v[m * Cfg::R2 + k2];
+      RegFFT<Cfg::R2, +1>::run(b);
+#pragma unroll
+      for (int n2 = 0; n2 < Cfg::R2; ++n2) stg[k1 * Cfg::STG_STRIDE + n2] = b[n2];
+    }
+  }
+}
+template <class Cfg> FAVAE_HD void inv_stage2(ThreadRegs<Cfg>& r, int t, const float2* stg) {
+  if constexpr (Cfg::R2 > 1) {
+#pragma unroll
+    for (int k1 = 0; k1 < Cfg::R1; ++k1) {
+      float2 y = stg[k1 * Cfg::STG_STRIDE + t];
+      r.v[k1] = (k1 == 0) ? y : cmul(y, make_float2(r.tw[k1].x, -r.tw[k1].y));
+    }
+  }
+  RegFFT<Cfg::R1, +1>::run(r.v);
+}
+
+}  // namespace favae

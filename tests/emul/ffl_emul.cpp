@@ -1,0 +1,65 @@
+// Host emulation of favae_b200/csrc/ffl_driver.cuh: the CUDA phases executed as plain
+// loops over (cta, tid).  TEST INFRASTRUCTURE -- validates the FFT index math, packing
+// and reductions on a machine without a GPU (tests/test_ffl_emulation.py).
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../favae_b200/csrc/ffl_configs.cuh"
+#include "../../favae_b200/csrc/ffl_driver.cuh"
+
+using namespace favae;
+
+template <class Cfg> struct HostEnv {
+  std::vector<ThreadRegs<Cfg>> regs_;
+  std::vector<float2> S_, stg_;
+  std::vector<float> fb_;
+  static constexpr int FB = 4 * Cfg::THREADS + 8 * Cfg::MPC + 8 * Cfg::C;
+  HostEnv()
+      : regs_(Cfg::C * Cfg::THREADS), S_((size_t)Cfg::C * Cfg::S_FLOAT2),
+        stg_((size_t)Cfg::C * Cfg::STG_FLOAT2), fb_((size_t)Cfg::C * FB) {
+    // poison so that reads of never-written slots show up
+    for (auto& z : S_) { z.x = NAN; z.y = NAN; }
+    for (auto& z : stg_) { z.x = NAN; z.y = NAN; }
+  }
+  template <class F> void for_threads(F f) {
+    for (int cta = 0; cta < Cfg::C; ++cta)
+      for (int tid = 0; tid < Cfg::THREADS; ++tid) f(cta, tid);
+  }
+  void sync_warp() {}
+  void sync_cta() {}
+  void sync_cluster() {}
+  ThreadRegs<Cfg>& regs(int cta, int tid) { return regs_[cta * Cfg::THREADS + tid]; }
+  float2* S(int, int owner) { return S_.data() + (size_t)owner * Cfg::S_FLOAT2; }
+  float2* stg(int cta) { return stg_.data() + (size_t)cta * Cfg::STG_FLOAT2; }
+  float* fbuf(int cta) { return fb_.data() + (size_t)cta * FB; }
+  float* cl(int, int owner) { return fbuf(owner) + 4 * Cfg::THREADS + 8 * Cfg::MPC; }
+  float2 twiddle(int j, int n) {
+    const double a = -2.0 * M_PI * (double)j / (double)n;
+    return make_float2((float)std::cos(a), (float)std::sin(a));
+  }
+};
+
+template <class Cfg> static void run(const FflParams& p) {
+  HostEnv<Cfg> env;
+  ffl_init_thread<Cfg>(env);
+  const long long batches = (p.maps + Cfg::MPC - 1) / Cfg::MPC;
+  for (long long b = 0; b < batches; ++b) ffl_map_batch<Cfg>(env, p, b);
+}
+
+extern "C" int ffl_emul(int n, const float* pred, const float* target, long long maps, float alpha,
+                        int log_matrix, float grad_scale, float* gp, float* gt, float* map_loss) {
+  FflParams p;
+  p.pred = pred; p.target = target; p.grad_pred = gp; p.grad_target = gt; p.map_loss = map_loss;
+  p.maps = maps; p.grad_scale = grad_scale; p.alpha = alpha; p.log_matrix = log_matrix;
+  switch (n) {
+    case 8: run<FflCfg8>(p); break;
+    case 16: run<FflCfg16>(p); break;
+    case 32: run<FflCfg32>(p); break;
+    case 64: run<FflCfg64>(p); break;
+    case 128: run<FflCfg128>(p); break;
+    case 256: run<FflCfg256>(p); break;
+    default: return -1;
+  }
+  return 0;
+}
