@@ -1,0 +1,66 @@
+// Shared host-side helpers of the C ABI: error reporting and launch accounting.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/favae_b200.h"
+
+namespace favae {
+
+char* last_error_buf();                 // thread-local, 512 bytes
+void count_launch(int n = 1);
+
+inline int fail(int code, const char* fmt, const char* a = "") {
+  snprintf(last_error_buf(), 512, fmt, a);
+  return code;
+}
+
+inline int check_launch(const char* what) {
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(last_error_buf(), 512, "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+#define FAVAE_CUDA_OK(expr)                                                          \
+  do {                                                                               \
+    cudaError_t e__ = (expr);                                                        \
+    if (e__ != cudaSuccess) {                                                        \
+      snprintf(favae::last_error_buf(), 512, "%s: %s", #expr, cudaGetErrorString(e__)); \
+      return (int)e__;                                                               \
+    }                                                                                \
+  } while (0)
+
+#define FAVAE_REQUIRE(cond, msg)                                  \
+  do {                                                            \
+    if (!(cond)) return favae::fail(-22, "favae_b200: %s", msg);  \
+  } while (0)
+
+inline int num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace favae

@@ -150,6 +150,9 @@ struct FflParams {
   float* grad_pred;         // nullable
   float* grad_target;       // nullable (written as -grad)
   float* map_loss;          // maps: sum_{u,v} w A^2 per map (unscaled by loss_weight / numel)
+  float* map_max;           // nullable: max_{u,v} f(A) of each map
+  const float* fmax_override;  // nullable: one device scalar used instead of the per-map max
+                               // (FocalFrequencyLoss batch_matrix=True)
   long long maps;
   float grad_scale;         // 2*loss_weight/numel / (N*N)
   float alpha;

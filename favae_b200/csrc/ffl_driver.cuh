@@ -184,7 +184,8 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       for (int i = 0; i < L; ++i) { s += fb[2 * T + m * TMAP + i]; mx = fmaxf(mx, fb[3 * T + m * TMAP + i]); }
       if (C == 1) {
         fb[4 * T + 2 * m] = s;
-        fb[4 * T + 2 * m + 1] = mx;
+        fb[4 * T + 2 * m + 1] = p.fmax_override ? p.fmax_override[0] : mx;
+        fb[4 * T + 2 * MPC + m] = mx;
       } else {
         for (int o = 0; o < C; ++o) {
           float* cl = env.cl(cta, o);
@@ -202,7 +203,8 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       float s = 0.f, mx = 0.f;
       for (int o = 0; o < C; ++o) { s += cl[2 * o]; mx = fmaxf(mx, cl[2 * o + 1]); }
       fb[4 * T] = s;
-      fb[4 * T + 1] = mx;
+      fb[4 * T + 1] = p.fmax_override ? p.fmax_override[0] : mx;
+      fb[4 * T + 2 * MPC] = mx;
     }
   });
   if (C > 1) env.sync_cta();
@@ -212,6 +214,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
     if (cta == 0 && j == 0 && map0 + m < p.maps) {
       const float s = fb[4 * T + 2 * m], mx = fb[4 * T + 2 * m + 1];
       p.map_loss[map0 + m] = (mx > 0.0f) ? s / mx : 0.0f;
+      if (p.map_max) p.map_max[map0 + m] = fb[4 * T + 2 * MPC + m];
     }
   });
   if (p.grad_pred == nullptr && p.grad_target == nullptr) {

@@ -1,0 +1,125 @@
+// CUDA instantiation of the fused spectrum-loss phases (ffl_driver.cuh) for sm_100a.
+// One CTA (N <= 128) or one 2-CTA cluster exchanging columns through distributed shared
+// memory (N = 256) owns a map from the first load to the gradient store: pred and target
+// are read once, both gradients written once, nothing else touches HBM.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "ffl_configs.cuh"
+#include "ffl_driver.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace favae {
+
+template <class Cfg> struct DevEnv {
+  ThreadRegs<Cfg> r;
+  float2* s_;
+  float2* stg_;
+  float* fb_;
+  int rank_;
+
+  template <class F> __device__ __forceinline__ void for_threads(F f) { f(rank_, (int)threadIdx.x); }
+  __device__ __forceinline__ void sync_warp() { __syncwarp(); }
+  __device__ __forceinline__ void sync_cta() { __syncthreads(); }
+  __device__ __forceinline__ void sync_cluster() {
+    if constexpr (Cfg::C == 1) __syncthreads();
+    else cg::this_cluster().sync();
+  }
+  __device__ __forceinline__ ThreadRegs<Cfg>& regs(int, int) { return r; }
+  __device__ __forceinline__ float2* S(int, int owner) {
+    if constexpr (Cfg::C == 1) return s_;
+    else return (owner == rank_) ? s_ : cg::this_cluster().map_shared_rank(s_, owner);
+  }
+  __device__ __forceinline__ float2* stg(int) { return stg_; }
+  __device__ __forceinline__ float* fbuf(int) { return fb_; }
+  __device__ __forceinline__ float* cl(int, int owner) {
+    float* base = fb_ + 4 * Cfg::THREADS + 8 * Cfg::MPC;
+    if constexpr (Cfg::C == 1) return base;
+    else return (owner == rank_) ? base : cg::this_cluster().map_shared_rank(base, owner);
+  }
+  __device__ __forceinline__ float2 twiddle(int j, int n) {
+    float s, c;
+    sincospif(-2.0f * (float)j / (float)n, &s, &c);
+    return make_float2(c, s);
+  }
+};
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS) ffl_kernel(const FflParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DevEnv<Cfg> env;
+  env.s_ = reinterpret_cast<float2*>(smem_raw);
+  env.stg_ = env.s_ + Cfg::S_FLOAT2;
+  env.fb_ = reinterpret_cast<float*>(env.stg_ + Cfg::STG_FLOAT2);
+  if constexpr (Cfg::C == 1) env.rank_ = 0;
+  else env.rank_ = (int)cg::this_cluster().block_rank();
+  ffl_init_thread<Cfg>(env);
+  const long long batches = (p.maps + Cfg::MPC - 1) / Cfg::MPC;
+  const long long stride = gridDim.x / Cfg::C;
+  for (long long b = blockIdx.x / Cfg::C; b < batches; b += stride) ffl_map_batch<Cfg>(env, p, b);
+}
+
+template <class Cfg> static int launch_ffl(const FflParams& p, cudaStream_t stream) {
+  static bool configured = false;
+  auto kern = ffl_kernel<Cfg>;
+  if (!configured) {
+    FAVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const long long batches = (p.maps + Cfg::MPC - 1) / Cfg::MPC;
+  int per_sm = (int)(200 * 1024 / Cfg::SMEM_BYTES);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm * Cfg::THREADS > 2048) per_sm = 2048 / Cfg::THREADS;
+  long long clusters = (long long)num_sms() * per_sm / Cfg::C;
+  if (clusters > batches) clusters = batches;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * Cfg::C));
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = Cfg::C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FAVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
+  return check_launch("ffl_kernel");
+}
+
+}  // namespace favae
+
+extern "C" {
+
+int favae_ffl_supported(int h, int w) {
+  return (h == w) && (h == 8 || h == 16 || h == 32 || h == 64 || h == 128 || h == 256);
+}
+
+int favae_ffl_forward(const float* pred, const float* target, int64_t maps, int h, int w,
+                      float alpha, int log_matrix, float grad_scale, float* map_loss,
+                      float* grad_pred, float* grad_target, float* map_max,
+                      const float* fmax_override, void* stream) {
+  using namespace favae;
+  FAVAE_REQUIRE(pred && target && map_loss, "ffl_forward: null pointer");
+  FAVAE_REQUIRE(favae_ffl_supported(h, w), "ffl_forward: maps must be square, side a power of two in [8,256]");
+  FAVAE_REQUIRE(maps >= 0, "ffl_forward: negative map count");
+  if (maps == 0) return 0;
+  FflParams p;
+  p.pred = pred; p.target = target; p.grad_pred = grad_pred; p.grad_target = grad_target;
+  p.map_loss = map_loss; p.maps = maps; p.alpha = alpha; p.log_matrix = log_matrix;
+  p.map_max = map_max; p.fmax_override = fmax_override;
+  p.grad_scale = grad_scale / (float)(h * w);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (h) {
+    case 8: return launch_ffl<FflCfg8>(p, s);
+    case 16: return launch_ffl<FflCfg16>(p, s);
+    case 32: return launch_ffl<FflCfg32>(p, s);
+    case 64: return launch_ffl<FflCfg64>(p, s);
+    case 128: return launch_ffl<FflCfg128>(p, s);
+    default: return launch_ffl<FflCfg256>(p, s);
+  }
+}
+}

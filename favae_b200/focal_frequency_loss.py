@@ -1,0 +1,119 @@
+"""Drop-in replacement for ``focal_frequency_loss.FocalFrequencyLoss`` (pip
+focal-frequency-loss==0.3.0; imported at /root/reference/favae_scripts/train_favae.py:27 and
+instantiated at :313,318,326) running as ONE fused sm_100a kernel per call.
+
+The reference transforms pred and target separately (2 complex FFTs), stacks real/imag,
+and runs ~15 elementwise / reduction kernels plus two host syncs (the ``.item()`` asserts).
+Here ``favae_ffl_forward`` reads pred and target once, transforms the *difference* with a
+half-spectrum real FFT held in shared memory, reduces the dynamic-weight statistics,
+applies the weight and the inverse transform in the same kernel and writes the gradients,
+so the backward pass is a no-op scale (include/favae_b200.h).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import _lib
+
+__all__ = ['FocalFrequencyLoss']
+
+
+class _FFLFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, pred, target, loss_weight, alpha, log_matrix, batch_matrix, mean_count, grad_mode):
+        maps = pred.numel() // (pred.shape[-1] * pred.shape[-2])
+        h, w = pred.shape[-2], pred.shape[-1]
+        need_p = grad_mode and ctx.needs_input_grad[0]
+        need_t = grad_mode and ctx.needs_input_grad[1]
+        gp = torch.empty_like(pred) if need_p else None
+        gt = torch.empty_like(target) if need_t else None
+        dev = pred.device
+        map_loss = torch.empty((max(maps, 1),), device=dev, dtype=torch.float32)
+        gscale = 2.0 * loss_weight / mean_count
+        st = _lib.stream()
+        if batch_matrix:
+            map_max = torch.empty((max(maps, 1),), device=dev, dtype=torch.float32)
+            _lib.call('favae_ffl_forward', _lib.ptr(pred), _lib.ptr(target), maps, h, w, alpha,
+                      int(log_matrix), 0.0, _lib.ptr(map_loss), None, None, _lib.ptr(map_max), None, st)
+            gmax = map_max[:maps].amax().reshape(1) if maps else torch.ones(1, device=dev)
+            _lib.call('favae_ffl_forward', _lib.ptr(pred), _lib.ptr(target), maps, h, w, alpha,
+                      int(log_matrix), gscale, _lib.ptr(map_loss), _lib.ptr(gp), _lib.ptr(gt), None,
+                      _lib.ptr(gmax), st)
+        else:
+            _lib.call('favae_ffl_forward', _lib.ptr(pred), _lib.ptr(target), maps, h, w, alpha,
+                      int(log_matrix), gscale, _lib.ptr(map_loss), _lib.ptr(gp), _lib.ptr(gt), None,
+                      None, st)
+        loss = torch.empty((1,), device=dev, dtype=torch.float32)
+        _lib.call('favae_sum_scaled', _lib.ptr(map_loss), maps, loss_weight / mean_count, _lib.ptr(loss), st)
+        ctx.gp, ctx.gt = gp, gt
+        ctx.prev_scale = None
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, go):
+        gp, gt = ctx.gp, ctx.gt
+        if gp is None and gt is None:
+            return (None,) * 8
+        go = go.detach().to(torch.float32).reshape(1).contiguous()
+        if ctx.prev_scale is not None:
+            # second backward through the same graph: undo the previous scale, work on copies
+            s = go / ctx.prev_scale
+            gp = gp.clone() if gp is not None else None
+            gt = gt.clone() if gt is not None else None
+        else:
+            s = go
+        ctx.prev_scale = go.clone() if ctx.prev_scale is None else ctx.prev_scale
+        a, b = (gp, gt) if gp is not None else (gt, None)
+        # grads were written by the forward kernel; this is a no-op unless go != 1
+        _lib.call('favae_scale_inplace', _lib.ptr(a), _lib.ptr(b), a.numel(), _lib.ptr(s), _lib.stream())
+        return gp, gt, None, None, None, None, None, None
+
+
+class FocalFrequencyLoss(nn.Module):
+    """Same constructor and ``forward(pred, target, matrix=None)`` as the pip package.
+
+    The reference only ever uses ``(loss_weight=w, alpha=1.0)``; ``patch_factor``,
+    ``ave_spectrum``, ``log_matrix`` and ``batch_matrix`` are supported as well.  A predefined
+    ``matrix`` is not (FA-VAE never passes one) and raises NotImplementedError.
+    """
+
+    def __init__(self, loss_weight=1.0, alpha=1.0, patch_factor=1, ave_spectrum=False,
+                 log_matrix=False, batch_matrix=False):
+        super().__init__()
+        self.loss_weight = loss_weight
+        self.alpha = alpha
+        self.patch_factor = patch_factor
+        self.ave_spectrum = ave_spectrum
+        self.log_matrix = log_matrix
+        self.batch_matrix = batch_matrix
+
+    def _patches(self, x):
+        # tensor2freq's crop-and-stack: (N,C,H,W) -> (N, P, C, H/p, W/p)
+        pf = self.patch_factor
+        n, c, h, w = x.shape
+        assert h % pf == 0 and w % pf == 0, 'Patch factor should be divisible by image height and width'
+        if pf == 1:
+            return x.unsqueeze(1)
+        ph, pw = h // pf, w // pf
+        return x.view(n, c, pf, ph, pf, pw).permute(0, 2, 4, 1, 3, 5).reshape(n, pf * pf, c, ph, pw)
+
+    def forward(self, pred, target, matrix=None, **kwargs):
+        if matrix is not None:
+            raise NotImplementedError('favae_b200: a predefined spectrum weight matrix is not supported')
+        _lib.require_cuda(pred, target)
+        if pred.shape != target.shape or pred.dim() != 4:
+            raise RuntimeError(f'expected two (N,C,H,W) tensors of equal shape, got {tuple(pred.shape)} '
+                               f'and {tuple(target.shape)}')
+        p, t = self._patches(pred.float()), self._patches(target.float())
+        if self.ave_spectrum:
+            # the FFT is linear: the mean spectrum is the spectrum of the batch mean
+            p, t = p.mean(0, keepdim=True), t.mean(0, keepdim=True)
+        h, w = p.shape[-2:]
+        if not _lib.load().favae_ffl_supported(h, w):
+            raise NotImplementedError(f'favae_b200: spectrum loss needs square power-of-two maps with side '
+                                      f'in [8, 256], got {h}x{w}')
+        p, t = p.contiguous(), t.contiguous()
+        return _FFLFunction.apply(p, t, float(self.loss_weight), float(self.alpha), bool(self.log_matrix),
+                                  bool(self.batch_matrix), float(p.numel()), torch.is_grad_enabled())

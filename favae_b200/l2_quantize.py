@@ -1,0 +1,349 @@
+"""Drop-in replacement for ``/root/reference/models/l2_quantize.py`` on B200.
+
+Same module names, constructor arguments, ``forward`` return values and ``state_dict`` keys
+(``_codebook.initted``, ``_codebook.cluster_size``, ``_codebook.embed`` [+ ``_codebook.embed_avg``,
+``project_in.*``, ``project_out.*``]) as the reference, so ``models/vqgan_fcm.py:100-105,115`` and
+``models/txt_cond_transformer.py:136,165`` keep working and published checkpoints load.
+
+Everything on the hot path runs in hand-written sm_100a kernels behind the C ABI in
+``include/favae_b200.h``:
+
+  row l2norm + NCHW rearrange  -> favae_vq_prepare_rows      (l2_quantize.py:403,408,540)
+  similarity GEMM + argmax     -> favae_vq_search_tc / _exact (:410-411, :280-282)
+  gather + straight-through    -> favae_vq_gather_st          (:415, :554, :560)
+  bincount + one-hot GEMM      -> favae_vq_code_stats         (:412, :418, :426)
+  EMA / normalise / where      -> favae_vq_ema_update_*       (:421-438, :292-300)
+  autograd backward            -> favae_vq_backward
+
+The two all-reduces of the reference (:419, :427) become ONE all-reduce of the flat
+``[bins | embed_sum]`` buffer.  There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as distributed
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib
+
+__all__ = ['VectorQuantize', 'CosineSimCodebook', 'EuclideanCodebook', 'l2norm', 'orthogonal_loss_fn']
+
+
+def exists(val):
+    return val is not None
+
+
+def default(val, d):
+    return val if exists(val) else d
+
+
+def l2norm(t):
+    return F.normalize(t, p=2, dim=-1)
+
+
+def uniform_init(*shape):
+    t = torch.empty(shape)
+    nn.init.kaiming_uniform_(t)
+    return t
+
+
+def orthogonal_loss_fn(t):
+    """l2_quantize.py:174-179.  Cold option (no published FA-VAE config enables it): plain
+    library GEMM on the normalised codes."""
+    h, n = t.shape[:2]
+    normed = l2norm(t)
+    identity = torch.eye(n, device=t.device).expand(h, n, n)
+    cosine_sim = torch.einsum('h i d, h j d -> h i j', normed, normed)
+    return ((cosine_sim - identity) ** 2).sum() / (h * n ** 2)
+
+
+def _search_mode():
+    import os
+    return os.environ.get('FAVAE_VQ_SEARCH', 'auto')
+
+
+class _QuantizeFunction(torch.autograd.Function):
+    """(x) -> (out, loss_sum) with d/dx = g_out + coef * (x - out) * g_loss."""
+
+    @staticmethod
+    def forward(ctx, x, codebook, hw, straight_through, want_loss):
+        n = x.numel() // codebook.dim
+        out, idx, loss_sum = codebook._search_and_gather(x, n, hw, straight_through, want_loss)
+        ctx.save_for_backward(x, out)
+        ctx.mark_non_differentiable(idx)
+        return out, idx, loss_sum
+
+    @staticmethod
+    def backward(ctx, g_out, _g_idx, g_loss):
+        x, out = ctx.saved_tensors
+        gx = torch.empty_like(x)
+        g_out = g_out.contiguous() if g_out is not None else None
+        g_loss = g_loss.contiguous() if g_loss is not None else None
+        _lib.call('favae_vq_backward', _lib.ptr(x), _lib.ptr(out), _lib.ptr(g_out), _lib.ptr(g_loss),
+                  x.numel(), 2.0, _lib.ptr(gx), _lib.stream())
+        return gx, None, None, None, None
+
+
+class _CodebookBase(nn.Module):
+    """Shared machinery of the two codebook classes (reference :183-306 and :308-444)."""
+
+    cosine = True
+
+    def __init__(self, dim, codebook_size, num_codebooks=1, kmeans_init=False, kmeans_iters=10,
+                 decay=0.8, eps=1e-5, threshold_ema_dead_code=2, use_ddp=False,
+                 learnable_codebook=False, sample_codebook_temp=0.):
+        super().__init__()
+        if num_codebooks != 1:
+            raise NotImplementedError('favae_b200: multi-head / multiple codebooks are not built '
+                                      '(never used by FA-VAE, models/vqgan_fcm.py:103-105)')
+        if kmeans_init:
+            raise NotImplementedError('favae_b200: kmeans_init is not built (always False in FA-VAE)')
+        if sample_codebook_temp != 0:
+            raise NotImplementedError('favae_b200: gumbel sampling (sample_codebook_temp > 0) is not built')
+        if threshold_ema_dead_code != 0:
+            raise NotImplementedError('favae_b200: dead-code expiry (threshold_ema_dead_code > 0) is not built')
+        self.dim = dim
+        self.decay = decay
+        self.codebook_size = codebook_size
+        self.num_codebooks = num_codebooks
+        self.kmeans_iters = kmeans_iters
+        self.eps = eps
+        self.threshold_ema_dead_code = threshold_ema_dead_code
+        self.sample_codebook_temp = sample_codebook_temp
+        self.use_ddp = use_ddp
+        self.learnable_codebook = learnable_codebook
+
+        embed = uniform_init(num_codebooks, codebook_size, dim)
+        if self.cosine:
+            embed = l2norm(embed)
+        self.register_buffer('initted', torch.Tensor([True]))
+        self.register_buffer('cluster_size', torch.zeros(num_codebooks, codebook_size))
+        if not self.cosine:
+            self.register_buffer('embed_avg', embed.clone())
+        if learnable_codebook:
+            self.embed = nn.Parameter(embed)
+        else:
+            self.register_buffer('embed', embed)
+
+    # -- kernels --------------------------------------------------------------------------
+    def _prepare(self, x, n, hw, normalize, half):
+        d = self.dim
+        xn = torch.empty((n, d), device=x.device, dtype=torch.float32)
+        xh = torch.empty((n, d), device=x.device, dtype=torch.float16) if half else None
+        _lib.call('favae_vq_prepare_rows', _lib.ptr(x), n, d, hw, int(normalize), _lib.ptr(xn),
+                  _lib.ptr(xh), None, _lib.stream())
+        return xn, xh
+
+    def _search_and_gather(self, x, n, hw, straight_through, want_loss):
+        k, d, dev = self.codebook_size, self.dim, x.device
+        embed = self.embed.detach()[0]
+        if not embed.is_contiguous():
+            raise RuntimeError('favae_b200: codebook buffer must be contiguous')
+        mode = _search_mode()
+        use_tc = self.cosine and mode != 'exact' and d % 64 == 0 and k % 128 == 0 and _tc_available()
+        if mode == 'tc' and not use_tc:
+            raise RuntimeError('favae_b200: FAVAE_VQ_SEARCH=tc but the tensor-core search does not '
+                               f'support dim={d}, codebook_size={k}')
+        idx = torch.empty((n,), device=dev, dtype=torch.int64)
+        keys = torch.empty((n,), device=dev, dtype=torch.int64)
+        if self.cosine:
+            xn, xh = self._prepare(x, n, hw, True, use_tc)
+            en, eh = self._prepare(embed, k, 1, True, use_tc)
+            if use_tc:
+                ws_bytes = _lib.load().favae_vq_search_tc_workspace_bytes(n, k, d)
+                ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
+                _lib.call('favae_vq_search_tc', _lib.ptr(xh), _lib.ptr(eh), _lib.ptr(xn), _lib.ptr(en),
+                          n, k, d, _lib.ptr(ws), ws_bytes, _lib.ptr(keys), _lib.ptr(idx), _lib.stream())
+            else:
+                _lib.call('favae_vq_search_exact', _lib.ptr(xn), _lib.ptr(en), None, n, k, d, 0,
+                          _lib.ptr(keys), _lib.ptr(idx), _lib.stream())
+        else:
+            xn, _ = self._prepare(x, n, hw, False, False)          # rearranged copy of x
+            esq = torch.empty((k,), device=dev, dtype=torch.float32)
+            en = torch.empty((k, d), device=dev, dtype=torch.float32)
+            _lib.call('favae_vq_prepare_rows', _lib.ptr(embed), k, d, 1, 0, _lib.ptr(en), None,
+                      _lib.ptr(esq), _lib.stream())
+            _lib.call('favae_vq_search_exact', _lib.ptr(xn), _lib.ptr(en), _lib.ptr(esq), n, k, d, 1,
+                      _lib.ptr(keys), _lib.ptr(idx), _lib.stream())
+
+        out = torch.empty_like(x)
+        loss_sum = torch.zeros((1,), device=dev, dtype=torch.float32)
+        blocks = (n + 31) // 32 if hw == 1 else (n // hw) * ((hw + 31) // 32)
+        partials = torch.empty((max(blocks, 1),), device=dev, dtype=torch.float32) if want_loss else None
+        _lib.call('favae_vq_gather_st', _lib.ptr(x), _lib.ptr(embed), _lib.ptr(idx), n, k, d, hw,
+                  int(straight_through), _lib.ptr(out), _lib.ptr(partials),
+                  _lib.ptr(loss_sum) if want_loss else None, _lib.stream())
+
+        if self.training:
+            stats = torch.empty((k * (d + 1),), device=dev, dtype=torch.float32)
+            _lib.call('favae_vq_code_stats', _lib.ptr(xn), _lib.ptr(idx), n, k, d, _lib.ptr(stats),
+                      _lib.stream())
+            if self.use_ddp:
+                # one all-reduce of [bins | embed_sum] (reference: two, :419/:427 and :291/:295)
+                distributed.all_reduce(stats)
+            self._ema_update(en, stats)
+        return out, idx, loss_sum
+
+    def _ema_update(self, en, stats):
+        raise NotImplementedError
+
+    # -- reference-compatible codebook call: x (..., d) -> (quantize, embed_ind) --------------
+    @torch.no_grad()
+    def forward(self, x):
+        _lib.require_cuda(x)
+        x = x.float().contiguous()
+        shape = x.shape
+        n = x.numel() // self.dim
+        out, idx, _ = self._search_and_gather(x, n, 1, False, False)
+        return out.view(shape), idx.view(shape[:-1])
+
+
+class CosineSimCodebook(_CodebookBase):
+    """l2_quantize.py:308-444."""
+    cosine = True
+
+    def _ema_update(self, en, stats):
+        _lib.call('favae_vq_ema_update_cosine', _lib.ptr(self.embed.data), _lib.ptr(self.cluster_size),
+                  _lib.ptr(en), _lib.ptr(stats), self.codebook_size, self.dim, float(self.decay),
+                  _lib.stream())
+
+
+class EuclideanCodebook(_CodebookBase):
+    """l2_quantize.py:183-306, including the quirk that ``embed_avg`` is never refreshed (:294-300)."""
+    cosine = False
+
+    def _ema_update(self, en, stats):
+        scratch = torch.empty((2,), device=stats.device, dtype=torch.float32)
+        _lib.call('favae_vq_ema_update_euclid', _lib.ptr(self.embed.data), _lib.ptr(self.cluster_size),
+                  _lib.ptr(self.embed_avg), _lib.ptr(stats), self.codebook_size, self.dim,
+                  float(self.decay), float(self.eps), _lib.ptr(scratch), _lib.stream())
+
+
+_TC = None
+
+
+def _tc_available():
+    global _TC
+    if _TC is None:
+        _TC = _lib.load().favae_vq_search_tc_workspace_bytes(128, 128, 64) > 0
+    return _TC
+
+
+class VectorQuantize(nn.Module):
+    """l2_quantize.py:448-596 -- same signature, same return triple ``(quantize, embed_ind, loss)``."""
+
+    def __init__(self, dim, codebook_size, codebook_dim=None, heads=1, separate_codebook_per_head=False,
+                 decay=0.8, eps=1e-5, kmeans_init=False, kmeans_iters=10, use_cosine_sim=False,
+                 threshold_ema_dead_code=0, channel_last=True, accept_image_fmap=False,
+                 commitment_weight=1., orthogonal_reg_weight=0., orthogonal_reg_active_codes_only=False,
+                 orthogonal_reg_max_codes=None, sample_codebook_temp=0., sync_codebook=False):
+        super().__init__()
+        if heads != 1 or separate_codebook_per_head:
+            raise NotImplementedError('favae_b200: heads > 1 is not built (FA-VAE uses heads=1)')
+        self.heads = heads
+        self.separate_codebook_per_head = separate_codebook_per_head
+
+        codebook_dim = default(codebook_dim, dim)
+        codebook_input_dim = codebook_dim * heads
+        requires_projection = codebook_input_dim != dim
+        self.project_in = nn.Linear(dim, codebook_input_dim) if requires_projection else nn.Identity()
+        self.project_out = nn.Linear(codebook_input_dim, dim) if requires_projection else nn.Identity()
+
+        self.eps = eps
+        self.commitment_weight = commitment_weight
+        has_codebook_orthogonal_loss = orthogonal_reg_weight > 0
+        self.orthogonal_reg_weight = orthogonal_reg_weight
+        self.orthogonal_reg_active_codes_only = orthogonal_reg_active_codes_only
+        self.orthogonal_reg_max_codes = orthogonal_reg_max_codes
+
+        codebook_class = EuclideanCodebook if not use_cosine_sim else CosineSimCodebook
+        self._codebook = codebook_class(
+            dim=codebook_dim, num_codebooks=1, codebook_size=codebook_size, kmeans_init=kmeans_init,
+            kmeans_iters=kmeans_iters, decay=decay, eps=eps,
+            threshold_ema_dead_code=threshold_ema_dead_code, use_ddp=sync_codebook,
+            learnable_codebook=has_codebook_orthogonal_loss, sample_codebook_temp=sample_codebook_temp)
+        self.codebook_size = codebook_size
+        self.accept_image_fmap = accept_image_fmap
+        self.channel_last = channel_last
+
+    @property
+    def codebook(self):
+        return self._codebook.embed[0]
+
+    def get_codebook_entry(self, indices, shape):
+        """l2_quantize.py:518-530 as a row gather (no one-hot GEMM); ``shape`` is (B, h, w, C)."""
+        _lib.require_cuda(indices)
+        idx = indices.reshape(-1).to(torch.int64).contiguous()
+        embed = self._codebook.embed.detach()[0]
+        n, d, k = idx.numel(), embed.shape[-1], embed.shape[0]
+        if n and (int(idx.min()) < 0 or int(idx.max()) >= k):
+            raise IndexError('favae_b200: code index out of range')
+        if shape is not None:
+            b, h, w, c = shape
+            if c != d or b * h * w != n:
+                raise RuntimeError(f'shape {tuple(shape)} does not match {n} indices of dim {d}')
+            out = torch.empty((b, c, h, w), device=idx.device, dtype=torch.float32)
+            hw = h * w
+        else:
+            out = torch.empty((n, d), device=idx.device, dtype=torch.float32)
+            hw = 1
+        _lib.call('favae_vq_gather_rows', _lib.ptr(embed), _lib.ptr(idx), n, k, d, hw, _lib.ptr(out),
+                  _lib.stream())
+        return out
+
+    def forward(self, x):
+        _lib.require_cuda(x)
+        device = x.device
+        need_transpose = not self.channel_last and not self.accept_image_fmap
+        projected = not isinstance(self.project_in, nn.Identity)
+        cb = self._codebook
+        training = self.training
+
+        if self.accept_image_fmap:
+            b, _, height, width = x.shape
+            if projected:
+                x = x.permute(0, 2, 3, 1).reshape(b, height * width, -1)      # :540
+                hw = 1
+            else:
+                hw = height * width          # the kernels address NCHW directly
+        else:
+            hw = 1
+            if need_transpose:
+                x = x.transpose(1, 2)        # 'b d n -> b n d'
+        x = self.project_in(x)
+        x = x.float().contiguous()
+        if x.shape[1 if hw > 1 else -1] != cb.dim:
+            raise RuntimeError(f'expected {cb.dim} channels, got {tuple(x.shape)}')
+
+        want_loss = training and self.commitment_weight > 0
+        if training:
+            quantize, idx, loss_sum = _QuantizeFunction.apply(x, cb, hw, True, want_loss)
+        else:
+            with torch.no_grad():
+                quantize, idx, loss_sum = _QuantizeFunction.apply(x, cb, hw, False, False)
+
+        loss = torch.zeros(1, device=device, requires_grad=training)            # :556
+        if training:
+            if want_loss:
+                loss = loss + loss_sum * (self.commitment_weight / x.numel())    # :560-561
+            if self.orthogonal_reg_weight > 0:                                  # :563-577
+                codebook = cb.embed
+                if self.orthogonal_reg_active_codes_only:
+                    codebook = codebook[:, torch.unique(idx)]
+                num_codes = codebook.shape[1]
+                if exists(self.orthogonal_reg_max_codes) and num_codes > self.orthogonal_reg_max_codes:
+                    rand_ids = torch.randperm(num_codes, device=device)[:self.orthogonal_reg_max_codes]
+                    codebook = codebook[:, rand_ids]
+                loss = loss + orthogonal_loss_fn(codebook) * self.orthogonal_reg_weight
+
+        quantize = self.project_out(quantize)
+        if self.accept_image_fmap:
+            if projected:
+                quantize = quantize.reshape(b, height, width, -1).permute(0, 3, 1, 2)
+            embed_ind = idx.view(b, height, width)
+        else:
+            if need_transpose:
+                quantize = quantize.transpose(1, 2)
+            embed_ind = idx.view(x.shape[:-1])
+        return quantize, embed_ind, loss

@@ -1,0 +1,41 @@
+"""Drop-in replacement for ``/root/reference/losses/vqgan_losses.py`` (same three functions,
+same arguments, same ``(loss (1,), [per-level scalars])`` returns, same in-place reversal of
+the caller's ``de_feat`` list).  The reference evaluates every level twice (:25-26, :45-46);
+here each level is evaluated once and the same tensor is returned in the list."""
+from __future__ import annotations
+
+import torch
+
+from .gaussian_blur import gaussian_blur_reflect
+
+__all__ = ['recon_ffl_loss', 'recon_ffl_features_loss', 'recon_sl_gaussian_features_loss']
+
+
+def recon_ffl_loss(ffl, x, x_recon):                                   # :13-14
+    return ffl(x_recon, x)
+
+
+def recon_ffl_features_loss(ffl, en_feat, de_feat, device):            # :18-30
+    de_feat.reverse()
+    loss = torch.zeros(1, device=device)
+    losses = []
+    for i in range(len(en_feat)):
+        level = ffl(de_feat[i], en_feat[i])
+        loss = loss + level
+        losses.append(level)
+    loss = loss / len(en_feat)
+    return loss, losses
+
+
+def recon_sl_gaussian_features_loss(ffl, gaussian_kernel, gaussian_sigma, en_feat, de_feat, device):  # :34-50
+    de_feat.reverse()
+    loss = torch.zeros(1, device=device)
+    losses = []
+    for i in range(len(en_feat)):
+        e = gaussian_blur_reflect(en_feat[i], float(gaussian_sigma), gaussian_kernel)
+        d = gaussian_blur_reflect(de_feat[i], float(gaussian_sigma), gaussian_kernel)
+        level = ffl(d, e)
+        loss = loss + level
+        losses.append(level)
+    loss = loss / len(en_feat)
+    return loss, losses

@@ -48,9 +48,11 @@ template <class Cfg> static void run(const FflParams& p) {
 }
 
 extern "C" int ffl_emul(int n, const float* pred, const float* target, long long maps, float alpha,
-                        int log_matrix, float grad_scale, float* gp, float* gt, float* map_loss) {
+                        int log_matrix, float grad_scale, float* gp, float* gt, float* map_loss,
+                        float* map_max, const float* fmax_override) {
   FflParams p;
   p.pred = pred; p.target = target; p.grad_pred = gp; p.grad_target = gt; p.map_loss = map_loss;
+  p.map_max = map_max; p.fmax_override = fmax_override;
   p.maps = maps; p.grad_scale = grad_scale; p.alpha = alpha; p.log_matrix = log_matrix;
   switch (n) {
     case 8: run<FflCfg8>(p); break;

@@ -1,0 +1,79 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol declared in
+include/favae_b200.h; the drop-in modules keep the reference's constructor, state_dict keys and
+error behaviour; nothing under favae_b200/ touches the oracle."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, 'include', 'favae_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(favae_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from favae_b200 import _lib
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 18
+    raw = ctypes.CDLL(_lib.lib_path())
+    for n in names:
+        assert hasattr(raw, n), f'{n} declared in include/favae_b200.h but not exported'
+        assert n in _lib.SIGNATURES, f'{n} has no ctypes signature'
+    assert lib.favae_abi_version() == 1
+    assert lib.favae_ffl_supported(256, 256) == 1 and lib.favae_ffl_supported(24, 24) == 0
+
+
+def test_state_dict_keys_match_reference():
+    from favae_b200 import VectorQuantize
+    vq = VectorQuantize(dim=256, codebook_size=1024, accept_image_fmap=True, use_cosine_sim=True)
+    sd = vq.state_dict()
+    assert set(sd) == {'_codebook.initted', '_codebook.cluster_size', '_codebook.embed'}
+    assert sd['_codebook.initted'].shape == (1,) and sd['_codebook.cluster_size'].shape == (1, 1024)
+    assert sd['_codebook.embed'].shape == (1, 1024, 256)
+    assert list(vq.parameters()) == []                         # train_favae.py:294 iterates this
+    torch.testing.assert_close(sd['_codebook.embed'].norm(dim=-1), torch.ones(1, 1024))
+    vq = VectorQuantize(dim=3, codebook_size=64, codebook_dim=32)          # Euclidean + projection
+    assert set(vq.state_dict()) == {'_codebook.initted', '_codebook.cluster_size', '_codebook.embed',
+                                    '_codebook.embed_avg', 'project_in.weight', 'project_in.bias',
+                                    'project_out.weight', 'project_out.bias'}
+    assert vq.codebook.shape == (64, 32)
+
+
+def test_no_cpu_fallback_and_unsupported_options():
+    from favae_b200 import FocalFrequencyLoss, VectorQuantize, gaussian_blur_reflect
+    vq = VectorQuantize(dim=8, codebook_size=16, accept_image_fmap=True, use_cosine_sim=True)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        vq(torch.zeros(1, 8, 2, 2))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        FocalFrequencyLoss()(torch.zeros(1, 1, 8, 8), torch.zeros(1, 1, 8, 8))
+    with pytest.raises(RuntimeError, match='CUDA'):
+        gaussian_blur_reflect(torch.zeros(1, 1, 8, 8), 1.0, 3)
+    for kw in (dict(heads=2), dict(kmeans_init=True), dict(sample_codebook_temp=1.0),
+               dict(threshold_ema_dead_code=2)):
+        with pytest.raises(NotImplementedError):
+            VectorQuantize(dim=8, codebook_size=16, **kw)
+
+
+def test_product_never_imports_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, 'favae_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(root, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', text, flags=re.M), f
+    alias = open(os.path.join(ROOT, 'focal_frequency_loss', '__init__.py')).read()
+    assert 'favae_b200' in alias and 'oracle' not in alias
+
+
+def test_patch_reference_installs_alias():
+    import favae_b200
+    done = favae_b200.patch_reference()
+    assert 'focal_frequency_loss' in done
+    from focal_frequency_loss import FocalFrequencyLoss
+    assert FocalFrequencyLoss is favae_b200.FocalFrequencyLoss

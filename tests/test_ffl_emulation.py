@@ -24,7 +24,7 @@ def emul():
     lib = ctypes.CDLL(so)
     lib.ffl_emul.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
                              ctypes.c_float, ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
-                             ctypes.c_void_p, ctypes.c_void_p]
+                             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     return lib
 
 
@@ -41,7 +41,7 @@ def test_emulated_kernel_matches_oracle(emul, n, maps, alpha, logm):
     lw = 0.5
     gs = 2 * lw / p.numel() / (n * n)
     assert emul.ffl_emul(n, p.data_ptr(), t.data_ptr(), maps, alpha, logm, gs,
-                         gp.data_ptr(), gt.data_ptr(), ml.data_ptr()) == 0
+                         gp.data_ptr(), gt.data_ptr(), ml.data_ptr(), None, None) == 0
     pd = p.double().requires_grad_(True); td = t.double().requires_grad_(True)
     ref = fo.focal_frequency_loss(pd, td, loss_weight=lw, alpha=alpha, log_matrix=bool(logm))
     ref.backward()
@@ -56,5 +56,27 @@ def test_emulated_identical_inputs(emul):
     p = torch.randn(3, 1, 16, 16)
     gp = torch.full_like(p, float('nan')); ml = torch.full((3,), float('nan'))
     assert emul.ffl_emul(16, p.data_ptr(), p.data_ptr(), 3, 1.0, 0, 1.0, gp.data_ptr(), None,
-                         ml.data_ptr()) == 0
+                         ml.data_ptr(), None, None) == 0
     assert torch.all(ml == 0) and torch.all(gp == 0)      # NaN -> 0 rule of the weight matrix
+
+
+def test_emulated_batch_matrix(emul):
+    """batch_matrix=True: one global maximum (two launches: statistics, then weighting)."""
+    n, maps, lw = 16, 6, 0.3
+    g = torch.Generator().manual_seed(11)
+    p = torch.randn(maps, 1, n, n, generator=g) * torch.arange(1, maps + 1).view(-1, 1, 1, 1)
+    t = torch.randn(maps, 1, n, n, generator=g)
+    ml = torch.empty(maps); mm = torch.empty(maps)
+    assert emul.ffl_emul(n, p.data_ptr(), t.data_ptr(), maps, 1.0, 0, 0.0, None, None,
+                         ml.data_ptr(), mm.data_ptr(), None) == 0
+    gmax = mm.max().reshape(1).contiguous()
+    gp = torch.empty_like(p)
+    gs = 2 * lw / p.numel() / (n * n)
+    assert emul.ffl_emul(n, p.data_ptr(), t.data_ptr(), maps, 1.0, 0, gs, gp.data_ptr(), None,
+                         ml.data_ptr(), None, gmax.data_ptr()) == 0
+    pd = p.double().requires_grad_(True)
+    ref = fo.focal_frequency_loss(pd, t.double(), loss_weight=lw, batch_matrix=True)
+    ref.backward()
+    loss = ml.double().sum() * lw / p.numel()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert (gp.double() - pd.grad).abs().max() <= 1e-5 * pd.grad.abs().max()

@@ -1,0 +1,159 @@
+"""GPU parity of the spectrum losses, the blur and the loss wrappers against the oracle and the
+golden fixtures (tolerance from BASELINE.json north_star: 1e-4 relative in fp32)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import blur_oracle as bo
+from oracle import ffl_oracle as fo
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def _run(shape, seed=0, **kw):
+    from favae_b200 import FocalFrequencyLoss
+    g = torch.Generator().manual_seed(seed)
+    p = torch.randn(*shape, generator=g); t = torch.randn(*shape, generator=g)
+    pg = p.cuda().requires_grad_(True); tg = t.cuda().requires_grad_(True)
+    loss = FocalFrequencyLoss(**kw)(pg, tg)
+    assert loss.dim() == 0
+    (loss * 1.0).backward()
+    pd = p.double().requires_grad_(True); td = t.double().requires_grad_(True)
+    ref = fo.focal_frequency_loss(pd, td, **kw)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= RTOL * abs(ref.item())
+    scale = pd.grad.abs().max()
+    assert (pg.grad.cpu().double() - pd.grad).abs().max() <= RTOL * scale
+    assert (tg.grad.cpu().double() - td.grad).abs().max() <= RTOL * scale
+
+
+@pytest.mark.parametrize('shape', [(2, 3, 8, 8), (3, 5, 16, 16), (2, 7, 32, 32), (2, 3, 64, 64),
+                                   (1, 3, 128, 128), (2, 3, 256, 256), (1, 37, 16, 16), (1, 130, 8, 8)])
+def test_ffl_matches_oracle(shape):
+    _run(shape, loss_weight=0.01, alpha=1.0)
+
+
+@pytest.mark.parametrize('kw', [dict(alpha=2.0), dict(alpha=0.5), dict(log_matrix=True),
+                                dict(batch_matrix=True), dict(patch_factor=2), dict(ave_spectrum=True),
+                                dict(patch_factor=2, batch_matrix=True, log_matrix=True)])
+def test_ffl_option_flags(kw):
+    _run((2, 3, 32, 32), seed=3, loss_weight=0.5, **kw)
+
+
+def test_ffl_baseline_feature_shapes():
+    """The four feature levels of the f=16 model at batch 1."""
+    for shape in [(1, 128, 256, 256), (1, 512, 16, 16), (1, 256, 16, 16)]:
+        _run(shape, loss_weight=0.01)
+
+
+def test_ffl_known_answers():
+    from favae_b200 import FocalFrequencyLoss
+    ffl = FocalFrequencyLoss(loss_weight=0.37)
+    p = torch.randn(2, 3, 64, 64, device='cuda')
+    assert float(ffl(p, p.clone())) == 0.0                                     # KAT0 (NaN -> 0)
+    assert float(ffl(p + 0.75, p)) == pytest.approx(0.37 * 0.75 ** 2, rel=1e-4)   # KAT1
+    H = W = 64
+    y, x = torch.meshgrid(torch.arange(H), torch.arange(W), indexing='ij')
+    d = (1.3 * torch.cos(2 * math.pi * (3 * x / W + 5 * y / H))).cuda()
+    z = torch.zeros(1, 1, H, W, device='cuda')
+    assert float(ffl(z + d, z)) == pytest.approx(0.37 * 1.3 ** 2 / 2, rel=1e-4)   # KAT2
+    t = torch.randn_like(p)
+    assert float(ffl(p, t)) <= 0.37 * float(((p - t) ** 2).mean()) * (1 + 1e-5)    # KAT3 Parseval
+    one = torch.zeros(1, 1, 64, 64, device='cuda'); one[0, 0, 3, 7] = 2.0
+    assert float(ffl(one, torch.zeros_like(one))) == pytest.approx(0.37 * 4.0 / 4096, rel=1e-4)  # KAT4
+    a, b = float(ffl(t + 3.0 * (p - t), t)), float(ffl(p, t))
+    assert a == pytest.approx(9.0 * b, rel=1e-4)                               # KAT5
+    s = torch.randn_like(p)
+    assert float(ffl(p + s, t + s)) == pytest.approx(b, rel=1e-3)              # KAT7
+
+
+def test_ffl_grad_scaling_and_no_grad():
+    from favae_b200 import FocalFrequencyLoss
+    ffl = FocalFrequencyLoss(loss_weight=1.0)
+    p = torch.randn(2, 3, 32, 32, device='cuda', requires_grad=True)
+    t = torch.randn(2, 3, 32, 32, device='cuda')
+    (ffl(p, t) * 0.25).backward()
+    g1 = p.grad.clone(); p.grad = None
+    ffl(p, t).backward()
+    torch.testing.assert_close(g1 * 4, p.grad, rtol=1e-6, atol=0)
+    with torch.no_grad():
+        v = ffl(p, t)
+    assert not v.requires_grad
+    with pytest.raises(NotImplementedError):
+        ffl(torch.randn(1, 1, 24, 24, device='cuda'), torch.randn(1, 1, 24, 24, device='cuda'))
+    with pytest.raises(RuntimeError):
+        ffl(torch.randn(1, 1, 16, 16), torch.randn(1, 1, 16, 16))              # CPU: no fallback
+
+
+def test_blur_matches_reference_fixture(golden_dir):
+    from favae_b200 import gaussian_blur_reflect
+    g = np.load(os.path.join(golden_dir, 'blur_cases.npz'))
+    for i in range(int(g['n'])):
+        x = torch.from_numpy(g[f'x{i}']).cuda().requires_grad_(True)
+        sig = torch.tensor([float(g[f'sigma{i}'])] * 4, device='cuda', requires_grad=True)
+        y = gaussian_blur_reflect(x, sig[1], int(g[f'k{i}']))
+        torch.testing.assert_close(y.cpu(), torch.from_numpy(g[f'y{i}']), rtol=1e-4, atol=1e-6)
+        (y * torch.from_numpy(g[f'go{i}']).cuda()).sum().backward()
+        torch.testing.assert_close(x.grad.cpu(), torch.from_numpy(g[f'gx{i}']), rtol=1e-4, atol=1e-6)
+        assert float(sig.grad[1]) == pytest.approx(float(g[f'gsig{i}']), rel=2e-3, abs=1e-5)
+        assert float(sig.grad[0]) == 0.0
+
+
+@pytest.mark.parametrize('shape,k', [((1, 4, 256, 256), 9), ((2, 8, 16, 16), 9), ((1, 3, 64, 64), 3),
+                                     ((1, 2, 40, 70), 15), ((1, 2, 33, 31), 5)])
+def test_blur_vs_oracle(shape, k):
+    from favae_b200 import gaussian_blur_reflect
+    g = torch.Generator().manual_seed(k)
+    x = torch.randn(*shape, generator=g); go = torch.randn(*shape, generator=g)
+    xd = x.double().requires_grad_(True); sd = torch.tensor(3.0, dtype=torch.float64, requires_grad=True)
+    yd = bo.gaussian_blur_reflect(xd, sd, k)
+    (yd * go.double()).sum().backward()
+    xg = x.cuda().requires_grad_(True); sg = torch.tensor(3.0, device='cuda', requires_grad=True)
+    y = gaussian_blur_reflect(xg, sg, k)
+    (y * go.cuda()).sum().backward()
+    assert (y.cpu().double() - yd).abs().max() <= RTOL * yd.abs().max()
+    assert (xg.grad.cpu().double() - xd.grad).abs().max() <= RTOL * xd.grad.abs().max()
+    assert float(sg.grad) == pytest.approx(float(sd.grad), rel=1e-3, abs=1e-4)
+
+
+def test_wrappers_match_reference_fixture(golden_dir):
+    from favae_b200 import FocalFrequencyLoss
+    from favae_b200 import vqgan_losses as vl
+    g = np.load(os.path.join(golden_dir, 'wrappers.npz'))
+    ffl = FocalFrequencyLoss(loss_weight=0.01, alpha=1.0)
+    en = [torch.from_numpy(g[f'en{i}']).cuda() for i in range(4)]
+    de = [torch.from_numpy(g[f'de{i}']).cuda() for i in range(4)]
+    d1 = list(de)
+    loss, lst = vl.recon_ffl_features_loss(ffl, list(en), d1, 'cuda')
+    assert d1[0] is de[-1] and loss.shape == (1,) and len(lst) == 4
+    np.testing.assert_allclose(loss.cpu().numpy(), g['dsl_loss'], rtol=RTOL)
+    np.testing.assert_allclose([float(v) for v in lst], g['dsl_list'], rtol=RTOL)
+    loss, lst = vl.recon_sl_gaussian_features_loss(ffl, 5, 3, list(en), list(de), 'cuda')
+    np.testing.assert_allclose(loss.cpu().numpy(), g['sl_loss'], rtol=RTOL)
+    np.testing.assert_allclose([float(v) for v in lst], g['sl_list'], rtol=RTOL)
+    v = vl.recon_ffl_loss(ffl, torch.from_numpy(g['img_x']).cuda(), torch.from_numpy(g['img_xr']).cuda())
+    np.testing.assert_allclose(float(v), float(g['img_loss']), rtol=RTOL)
+
+
+def test_dsl_gradients_reach_sigma_and_features():
+    """DSL: learnable-sigma blur feeding the spectrum loss, gradients checked against the oracle."""
+    from favae_b200 import FocalFrequencyLoss, gaussian_blur_reflect
+    g = torch.Generator().manual_seed(21)
+    e = torch.randn(1, 4, 64, 64, generator=g); d = torch.randn(1, 4, 64, 64, generator=g)
+    eg, dg = e.cuda().requires_grad_(True), d.cuda().requires_grad_(True)
+    s1 = torch.tensor(3.0, device='cuda', requires_grad=True); s2 = torch.tensor(2.0, device='cuda', requires_grad=True)
+    loss = FocalFrequencyLoss(loss_weight=0.01)(gaussian_blur_reflect(dg, s2, 9), gaussian_blur_reflect(eg, s1, 9))
+    loss.backward()
+    ed, dd = e.double().requires_grad_(True), d.double().requires_grad_(True)
+    t1 = torch.tensor(3.0, dtype=torch.float64, requires_grad=True); t2 = torch.tensor(2.0, dtype=torch.float64, requires_grad=True)
+    ref = fo.focal_frequency_loss(bo.gaussian_blur_reflect(dd, t2, 9), bo.gaussian_blur_reflect(ed, t1, 9), loss_weight=0.01)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= RTOL * abs(ref.item())
+    assert (eg.grad.cpu().double() - ed.grad).abs().max() <= RTOL * ed.grad.abs().max()
+    assert (dg.grad.cpu().double() - dd.grad).abs().max() <= RTOL * dd.grad.abs().max()
+    assert float(s1.grad) == pytest.approx(float(t1.grad), rel=2e-3)
+    assert float(s2.grad) == pytest.approx(float(t2.grad), rel=2e-3)
