@@ -54,7 +54,7 @@ vq_prepare_rows_kernel(const float* __restrict__ x, long long n, int d, long lon
       const float v = tile[r * ld + c] / denom;
       ss_out += v * v;
       if (xn) xn[(row0 + r) * d + c] = v;
-      if (xh) xh[(row0 + r) * d + c] = __float2half_rn(v);
+      if (xh) xh[(row0 + r) * d + c] = __float2half_rn(v * 16.0f);   // see vq_search_tc.cu (HALF_SCALE)
     }
     if (sq) {
       ss_out = warp_sum(ss_out);

@@ -1,12 +1,538 @@
-// Tensor-core (tcgen05 / TMEM / TMA) nearest-code search -- placeholder until the UMMA kernel
-// lands: reports "not available" through a zero workspace size so that callers take the exact
-// CUDA-core search.
+// Tensor-core nearest-code search for sm_100a: TMA -> shared memory -> tcgen05.mma (fp16 in,
+// fp32 accumulate in TMEM) -> tcgen05.ld epilogue that keeps, per latent, every code whose
+// approximate similarity is within a proven error bound of the running maximum.  The N x K
+// similarity matrix never exists in HBM (reference: einsum + argmax,
+// /root/reference/models/l2_quantize.py:410-411, materialises it twice).
+//
+// Exactness.  Latents and codes are L2-normalised in fp32, scaled by 16 and rounded to fp16
+// (favae_vq_prepare_rows).  With unit roundoff u = 2^-11 the error of one approximate
+// similarity is bounded by (2u + u^2)|x||e| plus the fp32 accumulation error, < 1.1e-3, so the
+// true fp32 arg-max always lies within TAU = 2.5e-3 of the approximate maximum.  Every code
+// inside that band is re-scored with an exact fp32 dot product (vq_rescore_kernel), ties go to
+// the lowest index.  Rows whose candidate list overflows (pathological ties, all-zero latents)
+// are searched exhaustively in fp32 (vq_fallback_kernel).  The result contract is therefore the
+// same as favae_vq_search_exact.
+//
+// Work decomposition.  A work item is (128-latent tile m, 256-code tile c).  Items are
+// linearised m-major and cut into equal contiguous ranges, one per CTA (persistent, 1 CTA/SM),
+// so every SM is busy even when there are fewer latent tiles than SMs.  A CTA's range is a short
+// list of segments (m, c_begin..c_end); each segment reports a per-row (max, candidates) record
+// into its own slot; the re-score kernel merges the slots of a row.
+//
+// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-7 epilogue (one TMEM lane = one latent per thread).  Pipelines: 4-stage smem ring
+// (TMA <-> MMA) and a double-buffered 2 x 256-column TMEM accumulator (MMA <-> epilogue).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
+namespace favae {
+namespace tc {
+
+constexpr int BM = 128;            // latents per tile (UMMA M)
+constexpr int BN = 256;            // codes per tile (UMMA N)
+constexpr int BK = 64;             // fp16 elements per 128-byte swizzle row
+constexpr int UK = 16;             // UMMA K for 16-bit inputs
+constexpr int STAGES = 4;
+constexpr int CAP = 8;             // candidate slots per latent and segment
+constexpr int MAX_KB = 4;          // d <= 256
+constexpr int THREADS = 256;
+constexpr float HALF_SCALE = 16.0f;                 // applied by prepare_rows to xh / eh
+constexpr float TAU = 2.5e-3f * HALF_SCALE * HALF_SCALE;   // band in units of the scaled product
+constexpr uint32_t A_KB_BYTES = BM * BK * 2;        // 16 KB
+constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;     // 32 KB
+// instruction descriptor: D=f32 (bit 4), A=B=f16 K-major, N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct Params {
+  long long n, k;
+  int d, kb;                       // kb = d / 64
+  int m_tiles, code_tiles;
+  long long pairs, per_cta;
+  int slots;
+  float* ws_max;                   // [m_tiles*128][slots]
+  int* ws_cnt;                     // [m_tiles*128][slots]   (-1 = overflow)
+  unsigned int* ws_idx;            // [m_tiles*128][slots][CAP]
+  float* ws_val;                   // [m_tiles*128][slots][CAP]
+  int* err;                        // device error word (pipeline timeout)
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a broken pipeline traps (error word set) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {     // ~2 s
+      if (err) atomicExch(err, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);          // start address
+  d |= (uint64_t)1 << 16;                            // leading byte offset (unused with swizzle)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset
+  d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+
+struct Segment { int m, c_begin, c_end, slot; };
+
+// segment `i` of this CTA's item range; returns false past the end
+__device__ __forceinline__ bool next_segment(const Params& p, long long& pair, long long end, Segment& s) {
+  if (pair >= end) return false;
+  s.m = (int)(pair / p.code_tiles);
+  s.c_begin = (int)(pair % p.code_tiles);
+  const long long left = end - pair;
+  s.c_end = (int)min((long long)p.code_tiles, (long long)s.c_begin + left);
+  const long long first_cta = ((long long)s.m * p.code_tiles) / p.per_cta;
+  s.slot = (int)((long long)blockIdx.x - first_cta);
+  pair += s.c_end - s.c_begin;
+  return true;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const Params p) {
+  extern __shared__ unsigned char smem_raw[];
+  // 128-byte-swizzle tiles need 1024-byte alignment
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // layout: A (MAX_KB x 16 KB) | B stages (4 x 32 KB) | candidate lists | barriers
+  unsigned char* a_base = smem;
+  unsigned char* b_base = smem + MAX_KB * A_KB_BYTES;
+  unsigned int* cand_idx = reinterpret_cast<unsigned int*>(b_base + STAGES * B_STAGE_BYTES);
+  float* cand_val = reinterpret_cast<float*>(cand_idx + BM * CAP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cand_val + BM * CAP);
+  // bars: full[4], empty[4], a_full, a_empty, tmem_full[2], tmem_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (4 + s); };
+  const uint32_t A_FULL = bar0 + 8u * 8, A_EMPTY = bar0 + 8u * 9;
+  auto T_FULL = [&](int s) { return bar0 + 8u * (10 + s); };
+  auto T_EMPTY = [&](int s) { return bar0 + 8u * (12 + s); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+    mbar_init(A_FULL, 1); mbar_init(A_EMPTY, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(T_FULL(s), 1); mbar_init(T_EMPTY(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long pair_begin = (long long)blockIdx.x * p.per_cta;
+  const long long pair_end = min(p.pairs, pair_begin + p.per_cta);
+
+  if (warp == 0 && lane == 0) {
+    // ================= TMA producer =================
+    int stage = 0;
+    uint32_t phase = 0, a_phase = 0;
+    long long pair = pair_begin;
+    Segment s;
+    while (next_segment(p, pair, pair_end, s)) {
+      mbar_wait(A_EMPTY, a_phase ^ 1, p.err, 1);
+      mbar_expect_tx(A_FULL, (uint32_t)p.kb * A_KB_BYTES);
+      for (int kb = 0; kb < p.kb; ++kb)
+        tma_load_2d(smem_u32(a_base + kb * A_KB_BYTES), &map_a, A_FULL, kb * BK, s.m * BM);
+      a_phase ^= 1;
+      for (int c = s.c_begin; c < s.c_end; ++c) {
+        for (int kb = 0; kb < p.kb; ++kb) {
+          mbar_wait(EMPTY(stage), phase ^ 1, p.err, 2);
+          mbar_expect_tx(FULL(stage), B_STAGE_BYTES);
+          tma_load_2d(smem_u32(b_base + stage * B_STAGE_BYTES), &map_b, FULL(stage), kb * BK, c * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ================= MMA issuer =================
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, a_phase = 0, acc_phase = 0;
+    long long pair = pair_begin;
+    Segment s;
+    while (next_segment(p, pair, pair_end, s)) {
+      mbar_wait(A_FULL, a_phase, p.err, 3);
+      a_phase ^= 1;
+      for (int c = s.c_begin; c < s.c_end; ++c) {
+        mbar_wait(T_EMPTY(acc), acc_phase ^ 1, p.err, 4);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * BN;
+        for (int kb = 0; kb < p.kb; ++kb) {
+          mbar_wait(FULL(stage), phase, p.err, 5);
+          tc_fence_after();
+          const uint64_t da = make_desc(smem_u32(a_base + kb * A_KB_BYTES));
+          const uint64_t db = make_desc(smem_u32(b_base + stage * B_STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            // advance both descriptors by k * 32 bytes inside the 128-byte swizzle row
+            tc_mma(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(EMPTY(stage));              // smem slot free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(T_FULL(acc));                 // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      tc_commit(A_EMPTY);                       // latent tile no longer read
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: running max + candidate band per latent =================
+    const int q = warp - 4;                     // TMEM lane quarter == warp_id % 4
+    const int row = q * 32 + lane;
+    unsigned int* my_idx = cand_idx + row * CAP;
+    float* my_val = cand_val + row * CAP;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    long long pair = pair_begin;
+    Segment s;
+    while (next_segment(p, pair, pair_end, s)) {
+      const long long grow = (long long)s.m * BM + row;
+      const bool active = grow < p.n;
+      float run = -INFINITY;
+      int cnt = 0;
+      bool overflow = false;
+      for (int c = s.c_begin; c < s.c_end; ++c) {
+        mbar_wait(T_FULL(acc), acc_phase, p.err, 6);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * BN;
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          float v[32];
+          tmem_ld32(taddr + ch * 32, v);
+          float t16[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) t16[j] = fmaxf(v[j], v[j + 16]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t16[j] = fmaxf(t16[j], t16[j + 8]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) t16[j] = fmaxf(t16[j], t16[j + 4]);
+          const float cmax = fmaxf(fmaxf(t16[0], t16[2]), fmaxf(t16[1], t16[3]));
+          const bool hit = active && !overflow && (cmax >= run - TAU);
+          if (__any_sync(0xffffffffu, hit)) {
+            if (hit) {
+              run = fmaxf(run, cmax);
+              const float thr = run - TAU;
+              const unsigned int code0 = (unsigned int)c * BN + ch * 32;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (v[j] >= thr) {
+                  if (cnt == CAP) {             // drop entries that fell out of the band
+                    int keep = 0;
+                    for (int i = 0; i < CAP; ++i) {
+                      const float pv = my_val[i];
+                      if (pv >= thr) { my_val[keep] = pv; my_idx[keep] = my_idx[i]; ++keep; }
+                    }
+                    cnt = keep;
+                  }
+                  if (cnt < CAP) { my_idx[cnt] = code0 + j; my_val[cnt] = v[j]; ++cnt; }
+                  else overflow = true;
+                }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(T_EMPTY(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      // publish this segment's record
+      const long long o = ((long long)s.m * BM + row) * p.slots + s.slot;
+      p.ws_max[o] = active ? run : -INFINITY;
+      p.ws_cnt[o] = active ? (overflow ? -1 : cnt) : 0;
+      for (int i = 0; i < cnt; ++i) { p.ws_idx[o * CAP + i] = my_idx[i]; p.ws_val[o * CAP + i] = my_val[i]; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + MAX_KB * A_KB_BYTES + STAGES * B_STAGE_BYTES +
+                              BM * CAP * 8 + 16 * 8 + 16;
+
+// ---------------------------------------------------------------- merge + exact re-score
+__device__ __forceinline__ unsigned int f_order(float f) {
+  unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(256)
+vq_rescore_kernel(const Params p, const float* __restrict__ xn, const float* __restrict__ en,
+                  long long* __restrict__ idx, int* __restrict__ ovf_count, int* __restrict__ ovf_rows) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.n) return;
+  const int m = (int)(row / BM);
+  // slots used by latent tile m
+  const long long c0 = ((long long)m * p.code_tiles) / p.per_cta;
+  const long long c1 = ((long long)(m + 1) * p.code_tiles - 1) / p.per_cta;
+  const int nslots = (int)(c1 - c0 + 1);
+  const long long base = row * p.slots;
+  float gmax = -INFINITY;
+  bool ovf = false;
+  for (int s = lane; s < nslots; s += 32) {
+    gmax = fmaxf(gmax, p.ws_max[base + s]);
+    ovf |= p.ws_cnt[base + s] < 0;
+  }
+  gmax = warp_max(gmax);
+  if (__any_sync(0xffffffffu, ovf)) {
+    if (lane == 0) ovf_rows[atomicAdd(ovf_count, 1)] = (int)row;
+    return;
+  }
+  const float thr = gmax - TAU;
+  unsigned long long best = 0ull;
+  const float* x = xn + row * p.d;
+  const int total = nslots * CAP;
+  for (int e0 = 0; e0 < total; e0 += 32) {
+    const int e = e0 + lane;
+    bool valid = false;
+    unsigned int code = 0;
+    if (e < total) {
+      const int s = e / CAP, i = e % CAP;
+      if (i < p.ws_cnt[base + s] && p.ws_val[(base + s) * CAP + i] >= thr) {
+        valid = true;
+        code = p.ws_idx[(base + s) * CAP + i];
+      }
+    }
+    unsigned int mask = __ballot_sync(0xffffffffu, valid);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const unsigned int cand = __shfl_sync(0xffffffffu, code, src);
+      const float* ev = en + (long long)cand * p.d;
+      float acc = 0.f;
+      for (int c = lane; c < p.d; c += 32) acc = fmaf(x[c], ev[c], acc);
+      acc = warp_sum(acc);
+      const unsigned long long key = ((unsigned long long)f_order(acc) << 32) | (0xFFFFFFFFu - cand);
+      best = key > best ? key : best;
+    }
+  }
+  if (lane == 0) idx[row] = (long long)(0xFFFFFFFFu - (unsigned int)(best & 0xFFFFFFFFull));
+}
+
+// exhaustive fp32 search of the (rare) rows whose candidate list overflowed: one block per row
+__global__ void __launch_bounds__(256)
+vq_fallback_kernel(const Params p, const float* __restrict__ xn, const float* __restrict__ en,
+                   long long* __restrict__ idx, const int* __restrict__ ovf_count,
+                   const int* __restrict__ ovf_rows) {
+  __shared__ unsigned long long wbest[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int count = *ovf_count;
+  for (int i = blockIdx.x; i < count; i += gridDim.x) {
+    const long long row = ovf_rows[i];
+    const float* x = xn + row * p.d;
+    unsigned long long best = 0ull;
+    for (long long code = warp; code < p.k; code += 8) {
+      const float* ev = en + code * p.d;
+      float acc = 0.f;
+      for (int c = lane; c < p.d; c += 32) acc = fmaf(x[c], ev[c], acc);
+      acc = warp_sum(acc);
+      const unsigned long long key = ((unsigned long long)f_order(acc) << 32) | (0xFFFFFFFFu - (unsigned int)code);
+      best = key > best ? key : best;
+    }
+    if (lane == 0) wbest[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long b = 0ull;
+      for (int w = 0; w < 8; ++w) b = wbest[w] > b ? wbest[w] : b;
+      idx[row] = (long long)(0xFFFFFFFFu - (unsigned int)(b & 0xFFFFFFFFull));
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, long long rows, int d, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(-38, "favae_b200: %s", "cuTensorMapEncodeTiled is unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)d * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-22, "favae_b200: %s", "cuTensorMapEncodeTiled failed");
+  return 0;
+}
+
+struct Plan {
+  int m_tiles, code_tiles, grid, slots;
+  long long pairs, per_cta;
+  size_t off_max, off_cnt, off_idx, off_val, off_ovf, total;
+};
+
+static Plan make_plan(long long n, long long k) {
+  Plan pl;
+  pl.m_tiles = (int)((n + BM - 1) / BM);
+  pl.code_tiles = (int)(k / BN);
+  pl.pairs = (long long)pl.m_tiles * pl.code_tiles;
+  long long g = num_sms();
+  if (g > pl.pairs) g = pl.pairs;
+  if (g < 1) g = 1;
+  pl.per_cta = (pl.pairs + g - 1) / g;
+  pl.grid = (int)((pl.pairs + pl.per_cta - 1) / pl.per_cta);
+  pl.slots = (int)((pl.code_tiles + pl.per_cta - 1) / pl.per_cta) + 1;
+  const size_t rows = (size_t)pl.m_tiles * BM;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t o = 0;
+  pl.off_max = o; o = al(o + rows * pl.slots * sizeof(float));
+  pl.off_cnt = o; o = al(o + rows * pl.slots * sizeof(int));
+  pl.off_idx = o; o = al(o + rows * pl.slots * CAP * sizeof(unsigned int));
+  pl.off_val = o; o = al(o + rows * pl.slots * CAP * sizeof(float));
+  pl.off_ovf = o; o = al(o + 256 + (size_t)n * sizeof(int));
+  pl.total = o;
+  return pl;
+}
+
+}  // namespace tc
+}  // namespace favae
+
+using namespace favae;
+
 extern "C" {
-size_t favae_vq_search_tc_workspace_bytes(int64_t, int64_t, int) { return 0; }
-int favae_vq_search_tc(const void*, const void*, const float*, const float*, int64_t, int64_t, int, void*,
-                       size_t, uint64_t*, int64_t*, void*) {
-  return favae::fail(-38, "favae_b200: %s", "vq_search_tc is not built in this library");
+
+size_t favae_vq_search_tc_workspace_bytes(int64_t n, int64_t k, int d) {
+  if (n <= 0 || k <= 0 || d <= 0 || d % tc::BK != 0 || d > tc::MAX_KB * tc::BK || k % tc::BN != 0 ||
+      k >= 0x7FFFFFFFll)
+    return 0;
+  return tc::make_plan(n, k).total;
+}
+
+int favae_vq_search_tc(const void* xh, const void* eh, const float* xn, const float* en, int64_t n,
+                       int64_t k, int d, void* workspace, size_t workspace_bytes, uint64_t* keys,
+                       int64_t* idx, void* stream) {
+  (void)keys;
+  FAVAE_REQUIRE(xh && eh && xn && en && idx && workspace, "vq_search_tc: null pointer");
+  FAVAE_REQUIRE(n > 0 && favae_vq_search_tc_workspace_bytes(n, k, d) > 0,
+                "vq_search_tc: needs d % 64 == 0, d <= 256, k % 256 == 0");
+  const tc::Plan pl = tc::make_plan(n, k);
+  FAVAE_REQUIRE(workspace_bytes >= pl.total, "vq_search_tc: workspace too small");
+  FAVAE_REQUIRE(((uintptr_t)xh % 16 == 0) && ((uintptr_t)eh % 16 == 0) && ((uintptr_t)workspace % 256 == 0),
+                "vq_search_tc: unaligned buffers");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUtensorMap map_a, map_b;
+  int rc = tc::make_map(&map_a, xh, n, d, tc::BM);
+  if (rc) return rc;
+  rc = tc::make_map(&map_b, eh, k, d, tc::BN);
+  if (rc) return rc;
+
+  unsigned char* ws = (unsigned char*)workspace;
+  tc::Params p;
+  p.n = n; p.k = k; p.d = d; p.kb = d / tc::BK;
+  p.m_tiles = pl.m_tiles; p.code_tiles = pl.code_tiles; p.pairs = pl.pairs; p.per_cta = pl.per_cta;
+  p.slots = pl.slots;
+  p.ws_max = (float*)(ws + pl.off_max);
+  p.ws_cnt = (int*)(ws + pl.off_cnt);
+  p.ws_idx = (unsigned int*)(ws + pl.off_idx);
+  p.ws_val = (float*)(ws + pl.off_val);
+  int* ovf_count = (int*)(ws + pl.off_ovf);
+  int* ovf_rows = ovf_count + 64;
+  p.err = ovf_count + 1;
+  FAVAE_CUDA_OK(cudaMemsetAsync(ovf_count, 0, 256, s));
+
+  static bool configured = false;
+  if (!configured) {
+    FAVAE_CUDA_OK(cudaFuncSetAttribute(tc::vq_search_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc::SMEM_BYTES));
+    configured = true;
+  }
+  tc::vq_search_tc_kernel<<<pl.grid, tc::THREADS, tc::SMEM_BYTES, s>>>(map_a, map_b, p);
+  rc = check_launch("vq_search_tc");
+  if (rc) return rc;
+  tc::vq_rescore_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(p, xn, en, (long long*)idx, ovf_count, ovf_rows);
+  rc = check_launch("vq_rescore");
+  if (rc) return rc;
+  tc::vq_fallback_kernel<<<num_sms(), 256, 0, s>>>(p, xn, en, (long long*)idx, ovf_count, ovf_rows);
+  return check_launch("vq_fallback");
 }
 }

@@ -141,7 +141,8 @@ class _CodebookBase(nn.Module):
         if not embed.is_contiguous():
             raise RuntimeError('favae_b200: codebook buffer must be contiguous')
         mode = _search_mode()
-        use_tc = self.cosine and mode != 'exact' and d % 64 == 0 and k % 128 == 0 and _tc_available()
+        use_tc = (self.cosine and mode != 'exact' and n > 0
+                  and _lib.load().favae_vq_search_tc_workspace_bytes(n, k, d) > 0)
         if mode == 'tc' and not use_tc:
             raise RuntimeError('favae_b200: FAVAE_VQ_SEARCH=tc but the tensor-core search does not '
                                f'support dim={d}, codebook_size={k}')
@@ -218,16 +219,6 @@ class EuclideanCodebook(_CodebookBase):
         _lib.call('favae_vq_ema_update_euclid', _lib.ptr(self.embed.data), _lib.ptr(self.cluster_size),
                   _lib.ptr(self.embed_avg), _lib.ptr(stats), self.codebook_size, self.dim,
                   float(self.decay), float(self.eps), _lib.ptr(scratch), _lib.stream())
-
-
-_TC = None
-
-
-def _tc_available():
-    global _TC
-    if _TC is None:
-        _TC = _lib.load().favae_vq_search_tc_workspace_bytes(128, 128, 64) > 0
-    return _TC
 
 
 class VectorQuantize(nn.Module):

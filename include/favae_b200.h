@@ -41,7 +41,8 @@ long long favae_launch_count(void);
 
 /* Row preparation: l2norm (l2_quantize.py:24-25, called at :403 and :408) fused with the
  * NCHW -> (N,D) rearrange (:540).  normalize == 0 copies instead (Euclidean codebook).
- * xn  (N*D fp32 row-major, nullable), xh (N*D fp16 row-major, nullable),
+ * xn  (N*D fp32 row-major, nullable), xh (N*D fp16 row-major, nullable; holds 16 * xn so that
+ * small components stay out of the fp16 subnormal range -- input of favae_vq_search_tc),
  * sq  (N fp32, nullable): sum of squares of the OUTPUT rows of xn. */
 int favae_vq_prepare_rows(const float* x, int64_t n, int d, int64_t hw, int normalize,
                           float* xn, void* xh, float* sq, void* stream);
@@ -58,7 +59,8 @@ int favae_vq_search_exact(const float* xn, const float* en, const float* e_sq, i
  * latent, every code whose approximate similarity is within a proven error bound of the
  * maximum, followed by an exact fp32 re-score of those candidates.  Same result contract as
  * favae_vq_search_exact with metric 0.  Needs xh/eh (fp16) and xn/en (fp32) from
- * favae_vq_prepare_rows.  d must be a multiple of 64, k a multiple of 128. */
+ * favae_vq_prepare_rows.  Supported when d % 64 == 0, d <= 256 and k % 256 == 0; the workspace
+ * query returns 0 otherwise (callers then use favae_vq_search_exact).  `keys` is unused. */
 size_t favae_vq_search_tc_workspace_bytes(int64_t n, int64_t k, int d);
 int favae_vq_search_tc(const void* xh, const void* eh, const float* xn, const float* en,
                        int64_t n, int64_t k, int d, void* workspace, size_t workspace_bytes,

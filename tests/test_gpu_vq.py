@@ -161,3 +161,62 @@ def test_edge_cases():
         VectorQuantize(dim=64, codebook_size=128, heads=2)
     with pytest.raises(NotImplementedError):
         VectorQuantize(dim=64, codebook_size=128, kmeans_init=True)
+
+
+def _tc_search(x, embed):
+    """Call the C ABI directly: prepare rows, tensor-core search, exact search."""
+    from favae_b200 import _lib
+    n, d = x.shape; k = embed.shape[0]
+    outs = {}
+    bufs = {}
+    for name, t, rows in (('x', x, n), ('e', embed, k)):
+        f32 = torch.empty(rows, d, device='cuda'); f16 = torch.empty(rows, d, device='cuda', dtype=torch.float16)
+        _lib.call('favae_vq_prepare_rows', t.data_ptr(), rows, d, 1, 1, f32.data_ptr(), f16.data_ptr(), None,
+                  _lib.stream())
+        bufs[name] = (f32, f16)
+    keys = torch.empty(n, device='cuda', dtype=torch.int64)
+    for mode in ('tc', 'exact'):
+        idx = torch.full((n,), -7, device='cuda', dtype=torch.int64)
+        if mode == 'tc':
+            nbytes = _lib.load().favae_vq_search_tc_workspace_bytes(n, k, d)
+            assert nbytes > 0
+            ws = torch.empty(nbytes, device='cuda', dtype=torch.uint8)
+            _lib.call('favae_vq_search_tc', bufs['x'][1].data_ptr(), bufs['e'][1].data_ptr(),
+                      bufs['x'][0].data_ptr(), bufs['e'][0].data_ptr(), n, k, d, ws.data_ptr(), nbytes,
+                      keys.data_ptr(), idx.data_ptr(), _lib.stream())
+        else:
+            _lib.call('favae_vq_search_exact', bufs['x'][0].data_ptr(), bufs['e'][0].data_ptr(), None, n, k, d, 0,
+                      keys.data_ptr(), idx.data_ptr(), _lib.stream())
+        torch.cuda.synchronize()
+        outs[mode] = idx
+    return outs
+
+
+@pytest.mark.parametrize('n,k,d', [(128, 256, 64), (100, 512, 128), (1000, 1024, 256), (4096, 16384, 256),
+                                   (37, 256, 192), (20000, 2048, 256)])
+def test_tensor_core_search_matches_exact_search(n, k, d):
+    torch.manual_seed(n + k)
+    x = torch.randn(n, d, device='cuda')
+    embed = torch.nn.functional.normalize(torch.randn(k, d, device='cuda'), dim=-1)
+    o = _tc_search(x, embed)
+    assert int(o['tc'].min()) >= 0 and int(o['tc'].max()) < k
+    _assert_indices(o['tc'], o['exact'], x, embed)
+    assert (o['tc'] != o['exact']).sum().item() <= max(1, n // 2000)
+
+
+def test_tensor_core_search_ties_duplicates_and_overflow():
+    torch.manual_seed(3)
+    k, d = 512, 64
+    embed = torch.nn.functional.normalize(torch.randn(k, d, device='cuda'), dim=-1)
+    embed[[5, 100, 300]] = embed[3].clone()         # 4 identical codes: inside the candidate band
+    embed[200:220] = embed[77].clone()              # 21 identical codes: candidate list overflows
+    x = torch.randn(300, d, device='cuda')
+    x[0] = embed[3] * 2.5                           # exact 4-way tie -> lowest index 3
+    x[1] = embed[77] * 0.3                          # 21-way tie -> exhaustive fallback -> 77
+    x[2] = 0.0                                      # all-zero latent: every code ties -> 0
+    x[3] = embed[300] + 1e-4 * torch.randn(d, device='cuda')
+    o = _tc_search(x, embed)
+    assert o['tc'][0].item() == 3 and o['tc'][1].item() == 77 and o['tc'][2].item() == 0
+    assert o['tc'][3].item() == 3
+    assert torch.equal(o['tc'][:4], o['exact'][:4])
+    _assert_indices(o['tc'], o['exact'], x, embed)
