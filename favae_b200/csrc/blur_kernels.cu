@@ -6,6 +6,7 @@
 // The reference builds the k x k outer product and runs a depthwise conv2d on the
 // reflect-padded map; the outer product of two identical 1-D Gaussians is applied here as
 // two 1-D passes over a shared-memory tile (same arithmetic up to fp32 rounding order).
+#include "blur_fast.cuh"
 #include "common.cuh"
 
 namespace favae {
@@ -214,7 +215,16 @@ using namespace favae;
 
 extern "C" {
 
-int64_t favae_blur_partials(int64_t maps, int h, int w) { return blur_blocks(maps, h, w); }
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+int64_t favae_blur_partials(int64_t maps, int h, int w) {
+  long long b = blur_blocks(maps, h, w);
+  if (w >= 4 && w <= 512 && (w & (w - 1)) == 0) {
+    const long long f = blurf::num_blocks(maps, h, w);
+    if (f > b) b = f;
+  }
+  return b;
+}
 
 static int blur_check(int64_t maps, int h, int w, int ksize) {
   FAVAE_REQUIRE(maps >= 0 && h > 0 && w > 0, "blur: bad shape");
@@ -229,6 +239,8 @@ int favae_blur_forward(const float* x, int64_t maps, int h, int w, int ksize, co
   FAVAE_REQUIRE(x && y && sigma, "blur_forward: null pointer");
   int rc = blur_check(maps, h, w, ksize);
   if (rc || maps == 0) return rc;
+  if (blurf::supported(h, w, ksize) && aligned16(x) && aligned16(y))
+    return blurf::launch<blurf::MODE_FWD>(x, nullptr, maps, h, w, ksize, sigma, y, nullptr, (cudaStream_t)stream);
   blur_forward_kernel<<<(unsigned)blur_blocks(maps, h, w), 256, 0, (cudaStream_t)stream>>>(x, h, w, ksize,
                                                                                          sigma, y);
   return check_launch("blur_forward");
@@ -244,6 +256,12 @@ int favae_blur_backward(const float* gy, const float* x, int64_t maps, int h, in
   if (maps == 0) {
     if (gsigma) FAVAE_CUDA_OK(cudaMemsetAsync(gsigma, 0, sizeof(float), s));
     return 0;
+  }
+  if (gx && blurf::supported(h, w, ksize) && aligned16(gy) && aligned16(gx) && (!gsigma || aligned16(x))) {
+    if (!gsigma) return blurf::launch<blurf::MODE_ADJ>(gy, nullptr, maps, h, w, ksize, sigma, gx, nullptr, s);
+    rc = blurf::launch<blurf::MODE_ADJ_SIG>(gy, x, maps, h, w, ksize, sigma, gx, partials, s);
+    if (rc) return rc;
+    return favae_sum_scaled(partials, blurf::num_blocks(maps, h, w), 1.0, gsigma, stream);
   }
   const unsigned blocks = (unsigned)blur_blocks(maps, h, w);
   if (gx) {

@@ -36,7 +36,8 @@ class _BlurFunction(torch.autograd.Function):
         gy = gy.contiguous()
         h, w = x.shape[-2:]
         maps = x.numel() // (h * w)
-        gx = torch.empty_like(x) if need_x else None
+        # the fused adjoint + sigma-gradient kernel always produces gx
+        gx = torch.empty_like(x) if (need_x or need_s) else None
         gs = partials = None
         if need_s:
             gs = torch.empty((1,), device=x.device, dtype=torch.float32)
@@ -45,7 +46,7 @@ class _BlurFunction(torch.autograd.Function):
         if need_x or need_s:
             _lib.call('favae_blur_backward', _lib.ptr(gy), _lib.ptr(x), maps, h, w, ctx.kernel_size,
                       _lib.ptr(sigma), _lib.ptr(gx), _lib.ptr(gs), _lib.ptr(partials), _lib.stream())
-        return gx, (gs.reshape(sigma.shape) if gs is not None else None), None
+        return (gx if need_x else None), (gs.reshape(sigma.shape) if gs is not None else None), None
 
 
 def gaussian_blur_reflect(x, sigma, kernel_size):

@@ -104,7 +104,11 @@ def test_blur_matches_reference_fixture(golden_dir):
 
 
 @pytest.mark.parametrize('shape,k', [((1, 4, 256, 256), 9), ((2, 8, 16, 16), 9), ((1, 3, 64, 64), 3),
-                                     ((1, 2, 40, 70), 15), ((1, 2, 33, 31), 5)])
+                                     ((1, 2, 40, 70), 15), ((1, 2, 33, 31), 5),
+                                     # streaming fast path: power-of-two widths, every kernel size
+                                     ((1, 2, 32, 32), 15), ((2, 3, 128, 128), 5), ((1, 2, 8, 8), 3),
+                                     ((1, 1, 512, 512), 11), ((3, 2, 64, 64), 9), ((1, 2, 48, 64), 9),
+                                     ((1, 2, 20, 16), 5), ((5, 7, 16, 16), 11), ((1, 2, 9, 8), 9)])
 def test_blur_vs_oracle(shape, k):
     from favae_b200 import gaussian_blur_reflect
     g = torch.Generator().manual_seed(k)
