@@ -95,10 +95,12 @@ class HotPath:
 
     def step(self, inp):
         blur = self.fb.gaussian_blur_reflect
-        z = inp['z'].requires_grad_(True)
-        x_recon = inp['x_recon'].requires_grad_(True)
-        enc = [t.requires_grad_(True) for t in inp['enc']]
-        dec = [t.requires_grad_(True) for t in inp['dec']]
+        # fresh leaves every step: in training these are activations, their gradients flow on to
+        # the backbone instead of being accumulated into a persistent .grad
+        z = inp['z'].detach().requires_grad_(True)
+        x_recon = inp['x_recon'].detach().requires_grad_(True)
+        enc = [t.detach().requires_grad_(True) for t in inp['enc']]
+        dec = [t.detach().requires_grad_(True) for t in inp['dec']]
         # ---- stage 0
         _, _, loss_q = self.vq(z)
         loss = COMMIT_W * loss_q.sum()
@@ -109,12 +111,13 @@ class HotPath:
         if ev is not None:
             # bracket the level-0 spectrum-loss call (the dominant kernel) with CUDA events
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            l0 = self.dsl(dec_b[3], enc_b[0])
-            b.record()
-            ev.append((a, b))
-            rest = [self.dsl(dec_b[2 - i], enc_b[1 + i]) for i in range(3)]
-            loss_dsl = (l0 + rest[0] + rest[1] + rest[2]).reshape(1) / 4
+            with self.fb.focal_frequency_loss.expected_upstream_scale(0.25):   # as the wrapper does
+                a.record()
+                l0 = self.dsl(dec_b[3], enc_b[0])
+                b.record()
+                ev.append((a, b))
+                rest = [self.dsl(dec_b[2 - i], enc_b[1 + i]) for i in range(3)]
+            loss_dsl = (l0 + rest[0] + rest[1] + rest[2]).reshape(1) * 0.25
         else:
             loss_dsl, _ = self.vl.recon_ffl_features_loss(self.dsl, enc_b, dec_b, self.device)
         loss = loss + loss_dsl.sum()

@@ -7,7 +7,7 @@
 // read once from HBM (strip halos hit L2), each output written once.
 //
 //   MODE_FWD      y  = H V x          reflect padding          (vqgan_fcm.py:35-41)
-//   MODE_ADJ      gx = H^T V^T gy     zero padding + the taps that reflect onto border rows/cols
+//   MODE_ADJ      gx = H^T V^T gy     forward data path + O(1) border corrections (see below)
 //   MODE_ADJ_SIG  MODE_ADJ plus  d/dsigma <gy, H V x> = <(H'^T V^T + H^T V'^T) gy, x>  with
 //                 k' = dk/dsigma, sharing the single sliding window over gy (x is read once,
 //                 without halo)                                (autograd of vqgan_fcm.py:20-41)
@@ -56,36 +56,13 @@ __device__ __forceinline__ void load_weights(const float* sigma_ptr, float* sk, 
   for (int t = 0; t < KS; ++t) { k[t] = sk[t]; dk[t] = sdk[t]; }
 }
 
-// static border fixes of the horizontal adjoint: column j within P of a border also receives the
-// taps of the padded columns that reflect onto it.  X0 / R0 are compile-time so every index is.
-template <int KS, int X0>
-__device__ __forceinline__ void left_fix(float (&o)[4], const float (&k)[KS], const float* line) {
-  constexpr int P = KS / 2;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    constexpr int dummy = 0; (void)dummy;
-    const int j = X0 + c;
-    if (j >= 1 && j <= P) {
-#pragma unroll
-      for (int s = 0; s < KS; ++s)
-        if (s >= j + P) o[c] = fmaf(k[s], line[LPAD + s - j - P], o[c]);
-    }
-  }
-}
-// thread owning columns w-4-R0 .. w-1-R0 (R0 = 0 or 4): distance from the right border jr = R0 + 3 - c
-template <int KS, int R0>
-__device__ __forceinline__ void right_fix(float (&o)[4], const float (&k)[KS], const float* line, int w) {
-  constexpr int P = KS / 2;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int jr = R0 + 3 - c;
-    if (jr >= 1 && jr <= P) {
-#pragma unroll
-      for (int s = 0; s < KS; ++s)
-        if (s <= P - jr) o[c] = fmaf(k[s], line[LPAD + w - 1 + jr - P + s], o[c]);
-    }
-  }
-}
+// Adjoint of (reflect-pad, correlate) without folding.  Writing the reflected samples explicitly,
+//   gx[j] = sum_q g[q] k[q-j+P]  +  [1 <= j <= P] sum_{o=0}^{P-j} g[o] k[P-j-o]   (+ mirror at the far border)
+// which is the FORWARD stencil on the mirrored extension of g, except that
+//   * the border sample itself (o = 0) is missing from the mirror:  gx[j] += k[P-j] g[0], 1 <= j <= P
+//   * the border output (j = 0) takes no mirrored taps at all.
+// So the adjoint reuses the forward data path (mirrored halos) plus these two O(1) corrections per
+// border, which keeps its instruction stream as short as the forward one.
 
 template <int KS, int TH, int MODE>
 __global__ void __launch_bounds__(THREADS)
@@ -114,117 +91,144 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ aux, i
   const float* base = src + map * (long long)h * w;
   float acc_sigma = 0.f;
 
-  float4 win[KS];
-#pragma unroll
-  for (int t = 0; t < KS; ++t) win[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-#pragma unroll
-  for (int r = 0; r < TH + KS - 1; ++r) {
-    // ---- vertical: slide one input row into the window
+  // Register ring of RS = KS + Q rows: the KS-row window of the vertical pass plus Q rows in flight
+  // from HBM (explicit prefetch: ~6 rows per thread are needed to cover the HBM latency at this
+  // occupancy).  The row loop is unrolled RS-fold so every ring index is a constant; unrolling all
+  // TH + KS - 1 rows overflows the instruction cache in the sigma-gradient variant.
+  constexpr int Q = 6 + ((3 - (KS + 6) % 3) % 3), RS = KS + Q, XQ = 3, NR = TH + KS - 1;
+  static_assert(RS % XQ == 0, "x prefetch ring must tile the unroll factor");
+  const long long mapoff = map * (long long)h * w;
+  auto load_row = [&](int r) -> float4 {
     const int yi = y0 - P + r;
     float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) {
-      if (ADJ) {
-        if (yi >= 0 && yi < h) in = ld4(base + (long long)yi * w + x0);
-      } else {
-        in = ld4(base + (long long)reflect_idx(yi, h) * w + x0);
-      }
-    }
-    win[r % KS] = in;
-    if (r < KS - 1) continue;
-    const int yo = y0 + r - (KS - 1);            // output row of this iteration
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), vd = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) in = ld4(base + (long long)reflect_idx(yi, h) * w + x0);
+    return in;
+  };
+  auto load_x = [&](int r) -> float4 {           // x row of the output produced at iteration r
+    const int yo = y0 + r - (KS - 1);
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (SIG && live && r >= KS - 1 && yo < h) xv = ld4(aux + mapoff + (long long)yo * w + x0);
+    return xv;
+  };
+  float4 ring[RS], xq[XQ];
 #pragma unroll
-    for (int t = 0; t < KS; ++t) {
-      const float4& wv = win[(r + 1 + t) % KS];  // input row yo - P + t
-      fma4(v, k[t], wv);
-      if (SIG) fma4(vd, dk[t], wv);
-    }
-    if (ADJ && live && yo < h) {
-      // rows within P of a border also receive the taps of the padded rows that reflect onto them
-      if (yo >= 1 && yo <= P) {
-        for (int rr = 0; rr <= P - yo; ++rr) {          // G(-yo): taps s = yo + P + rr, source row rr
-          if (rr < h) {
-            const float4 g = ld4(base + (long long)rr * w + x0);
-            fma4(v, sk[yo + P + rr], g);
-            if (SIG) fma4(vd, sdk[yo + P + rr], g);
-          }
-        }
-      }
-      if (yo >= h - 1 - P && yo <= h - 2) {
-        const int jr = h - 1 - yo;                      // G(h-1+jr): taps s = 0 .. P-jr, row h-1+jr-P+s
-        for (int s2 = 0; s2 <= P - jr; ++s2) {
-          const int rr = h - 1 + jr - P + s2;
-          if (rr >= 0) {
-            const float4 g = ld4(base + (long long)rr * w + x0);
-            fma4(v, sk[s2], g);
-            if (SIG) fma4(vd, sdk[s2], g);
-          }
-        }
-      }
-    }
-    // ---- horizontal through a shared line
-    float* line = lines + ((size_t)((r & 1) * groups + grp) * NV) * ll;
-    *reinterpret_cast<float4*>(line + LPAD + x0) = v;
-    if (SIG) *reinterpret_cast<float4*>(line + ll + LPAD + x0) = vd;
-    if (!ADJ) {
-      // mirrored halo entries (reflect): index -j <- j, index w-1+j <- w-1-j
-      const float vv[4] = {v.x, v.y, v.z, v.w};
+  for (int q = 0; q < RS; ++q) ring[q] = (q < Q) ? load_row(q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int j = x0 + c;
-        if (j >= 1 && j <= P) line[LPAD - j] = vv[c];
-        const int jr = w - 1 - j;
-        if (jr >= 1 && jr <= P) line[LPAD + w - 1 + jr] = vv[c];
-      }
-    } else {
-      if (tx == 0) {
+  for (int q = 0; q < XQ; ++q) xq[q] = load_x(q);
+  // FULL: all rows unrolled (fastest while the code fits the instruction cache: forward and plain
+  // adjoint); otherwise RS-fold unroll inside a rolled loop (sigma-gradient variant)
+  constexpr bool FULL = !SIG;
+  constexpr int STEP = FULL ? NR : RS;
+#pragma unroll 1
+  for (int r0 = 0; r0 < NR; r0 += STEP) {
 #pragma unroll
-        for (int j = 1; j <= LPAD; ++j) { line[LPAD - j] = 0.f; if (SIG) line[ll + LPAD - j] = 0.f; }
-      }
-      if (tx == tpi - 1) {
-#pragma unroll
-        for (int j = 1; j <= LPAD; ++j) { line[LPAD + w - 1 + j] = 0.f; if (SIG) line[ll + LPAD + w - 1 + j] = 0.f; }
-      }
-    }
-    __syncthreads();
-    float seg[4 + 2 * P], segd[SIG ? 4 + 2 * P : 1];
-#pragma unroll
-    for (int i = 0; i < 4 + 2 * P; ++i) {
-      seg[i] = line[LPAD + x0 - P + i];
-      if (SIG) segd[i] = line[ll + LPAD + x0 - P + i];
-    }
-    float o[4] = {0.f, 0.f, 0.f, 0.f}, z[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int uu = 0; uu < STEP; ++uu) {
+      const int r = r0 + uu;
+      const int u = uu % RS;
+      if (r >= NR) break;
+      if (r + Q < NR) ring[(u + Q) % RS] = load_row(r + Q);
+      const float4 xrow = xq[u % XQ];
+      if (SIG && r + XQ < NR) xq[u % XQ] = load_x(r + XQ);
+      if (r < KS - 1) continue;
+      const int yo = y0 + r - (KS - 1);            // output row of this iteration
+      // ---- vertical pass over the window rows yo - P .. yo + P
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f), vd = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool top = ADJ && yo == 0, bot = ADJ && yo == h - 1;   // border outputs: no mirrored taps
 #pragma unroll
       for (int t = 0; t < KS; ++t) {
-        o[c] = fmaf(k[t], seg[c + t], o[c]);
-        if (SIG) z[c] = fmaf(dk[t], seg[c + t], fmaf(k[t], segd[c + t], z[c]));
+        const float4& wv = ring[(u + RS - (KS - 1) + t) % RS];
+        const bool drop = (t < P && top) || (t > P && bot);
+        fma4(v, drop ? 0.f : k[t], wv);
+        if (SIG) fma4(vd, drop ? 0.f : dk[t], wv);
       }
-    }
-    if (ADJ) {
-      if (tx == 0) {
-        left_fix<KS, 0>(o, k, line);
-        if (SIG) { left_fix<KS, 0>(z, dk, line); left_fix<KS, 0>(z, k, line + ll); }
-      } else if (tx == 1 && P > 3) {
-        left_fix<KS, 4>(o, k, line);
-        if (SIG) { left_fix<KS, 4>(z, dk, line); left_fix<KS, 4>(z, k, line + ll); }
+      if (ADJ && live) {
+        if (yo >= 1 && yo <= P) {                        // missing border sample of the mirror
+          const float4 g = ld4(base + x0);
+          fma4(v, sk[P - yo], g);
+          if (SIG) fma4(vd, sdk[P - yo], g);
+        }
+        const int jr = h - 1 - yo;
+        if (jr >= 1 && jr <= P) {
+          const float4 g = ld4(base + (long long)(h - 1) * w + x0);
+          fma4(v, sk[P - jr], g);
+          if (SIG) fma4(vd, sdk[P - jr], g);
+        }
       }
-      if (tx == tpi - 1) {
-        right_fix<KS, 0>(o, k, line, w);
-        if (SIG) { right_fix<KS, 0>(z, dk, line, w); right_fix<KS, 0>(z, k, line + ll, w); }
-      } else if (tx == tpi - 2 && P > 3) {
-        right_fix<KS, 4>(o, k, line, w);
-        if (SIG) { right_fix<KS, 4>(z, dk, line, w); right_fix<KS, 4>(z, k, line + ll, w); }
+      // ---- horizontal pass through a shared line
+      float* line = lines + ((size_t)((r & 1) * groups + grp) * NV) * ll;
+      *reinterpret_cast<float4*>(line + LPAD + x0) = v;
+      if (SIG) *reinterpret_cast<float4*>(line + ll + LPAD + x0) = vd;
+      {
+        // mirrored halo entries (reflect): index -j <- j, index w-1+j <- w-1-j
+        const float vv[4] = {v.x, v.y, v.z, v.w}, vvd[4] = {vd.x, vd.y, vd.z, vd.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int j = x0 + c;
+          if (j >= 1 && j <= P) { line[LPAD - j] = vv[c]; if (SIG) line[ll + LPAD - j] = vvd[c]; }
+          const int jr = w - 1 - j;
+          if (jr >= 1 && jr <= P) { line[LPAD + w - 1 + jr] = vv[c]; if (SIG) line[ll + LPAD + w - 1 + jr] = vvd[c]; }
+        }
       }
-    }
-    if (live && yo < h) {
-      const long long a = map * (long long)h * w + (long long)yo * w + x0;
-      *reinterpret_cast<float4*>(dst + a) = make_float4(o[0], o[1], o[2], o[3]);
-      if (SIG) {
-        const float4 xv = ld4(aux + a);
-        acc_sigma = fmaf(xv.x, z[0], fmaf(xv.y, z[1], fmaf(xv.z, z[2], fmaf(xv.w, z[3], acc_sigma))));
+      __syncthreads();
+      float seg[4 + 2 * P], segd[SIG ? 4 + 2 * P : 1];
+#pragma unroll
+      for (int i = 0; i < 4 + 2 * P; ++i) {
+        seg[i] = line[LPAD + x0 - P + i];
+        if (SIG) segd[i] = line[ll + LPAD + x0 - P + i];
+      }
+      float o[4] = {0.f, 0.f, 0.f, 0.f}, z[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int t = 0; t < KS; ++t) {
+          o[c] = fmaf(k[t], seg[c + t], o[c]);
+          if (SIG) z[c] = fmaf(dk[t], seg[c + t], fmaf(k[t], segd[c + t], z[c]));
+        }
+      }
+      if (ADJ) {
+        if (tx == 0 || (tx == 1 && P > 3)) {
+          const float g0 = line[LPAD], gd0 = SIG ? line[ll + LPAD] : 0.f;
+          if (tx == 0) {
+            o[0] = 0.f; z[0] = 0.f;                      // column 0: only the taps inside the map
+#pragma unroll
+            for (int t = P; t < KS; ++t) {
+              o[0] = fmaf(k[t], seg[t], o[0]);
+              if (SIG) z[0] = fmaf(dk[t], seg[t], fmaf(k[t], segd[t], z[0]));
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {                  // columns 1..P: the border sample itself
+            const int j = x0 + c;
+            if (j >= 1 && j <= P) {
+              o[c] = fmaf(sk[P - j], g0, o[c]);
+              if (SIG) z[c] = fmaf(sdk[P - j], g0, fmaf(sk[P - j], gd0, z[c]));
+            }
+          }
+        }
+        if (tx == tpi - 1 || (tx == tpi - 2 && P > 3)) {
+          const float g0 = line[LPAD + w - 1], gd0 = SIG ? line[ll + LPAD + w - 1] : 0.f;
+          if (tx == tpi - 1) {
+            o[3] = 0.f; z[3] = 0.f;
+#pragma unroll
+            for (int t = 0; t <= P; ++t) {
+              o[3] = fmaf(k[t], seg[3 + t], o[3]);
+              if (SIG) z[3] = fmaf(dk[t], seg[3 + t], fmaf(k[t], segd[3 + t], z[3]));
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int jr = w - 1 - (x0 + c);
+            if (jr >= 1 && jr <= P) {
+              o[c] = fmaf(sk[P - jr], g0, o[c]);
+              if (SIG) z[c] = fmaf(sdk[P - jr], g0, fmaf(sk[P - jr], gd0, z[c]));
+            }
+          }
+        }
+      }
+      if (live && yo < h) {
+        *reinterpret_cast<float4*>(dst + mapoff + (long long)yo * w + x0) = make_float4(o[0], o[1], o[2], o[3]);
+        if (SIG)
+          acc_sigma = fmaf(xrow.x, z[0], fmaf(xrow.y, z[1], fmaf(xrow.z, z[2], fmaf(xrow.w, z[3], acc_sigma))));
       }
     }
   }

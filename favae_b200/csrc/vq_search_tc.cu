@@ -7,9 +7,10 @@
 // Exactness.  Latents and codes are L2-normalised in fp32, scaled by 16 and rounded to fp16
 // (favae_vq_prepare_rows).  With unit roundoff u = 2^-11 the error of one approximate
 // similarity is bounded by (2u + u^2)|x||e| plus the fp32 accumulation error, < 1.1e-3, so the
-// true fp32 arg-max always lies within TAU = 2.5e-3 of the approximate maximum.  Every code
-// inside that band is re-scored with an exact fp32 dot product (vq_rescore_kernel), ties go to
-// the lowest index.  Rows whose candidate list overflows (pathological ties, all-zero latents)
+// true fp32 arg-max always lies within TAU = 2.5e-3 of the approximate maximum.  The epilogue
+// works on 32-code chunks: every chunk whose maximum falls inside that band is recorded, and all
+// 32 codes of a recorded chunk are re-scored with exact fp32 dot products (vq_rescore_kernel,
+// same accumulation order as favae_vq_search_exact); ties go to the lowest index.  Rows whose candidate list overflows (pathological ties, all-zero latents)
 // are searched exhaustively in fp32 (vq_fallback_kernel).  The result contract is therefore the
 // same as favae_vq_search_exact.
 //
@@ -19,8 +20,9 @@
 // list of segments (m, c_begin..c_end); each segment reports a per-row (max, candidates) record
 // into its own slot; the re-score kernel merges the slots of a row.
 //
-// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
-// warps 4-7 epilogue (one TMEM lane = one latent per thread).  Pipelines: 4-stage smem ring
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-11 epilogue: one TMEM lane = one latent per thread, two warps per lane quarter, each
+// taking one 128-column half of the accumulator (two warps per scheduler hide TMEM latency).  Pipelines: 4-stage smem ring
 // (TMA <-> MMA) and a double-buffered 2 x 256-column TMEM accumulator (MMA <-> epilogue).
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -35,9 +37,10 @@ constexpr int BN = 256;            // codes per tile (UMMA N)
 constexpr int BK = 64;             // fp16 elements per 128-byte swizzle row
 constexpr int UK = 16;             // UMMA K for 16-bit inputs
 constexpr int STAGES = 4;
-constexpr int CAP = 8;             // candidate slots per latent and segment
+constexpr int CAP = 8;             // candidate chunk records per latent, segment and column half
 constexpr int MAX_KB = 4;          // d <= 256
-constexpr int THREADS = 256;
+constexpr int THREADS = 384;
+constexpr int EPI_WARPS = 8;
 constexpr float HALF_SCALE = 16.0f;                 // applied by prepare_rows to xh / eh
 constexpr float TAU = 2.5e-3f * HALF_SCALE * HALF_SCALE;   // band in units of the scaled product
 constexpr uint32_t A_KB_BYTES = BM * BK * 2;        // 16 KB
@@ -51,10 +54,11 @@ struct Params {
   int m_tiles, code_tiles;
   long long pairs, per_cta;
   int slots;
-  float* ws_max;                   // [m_tiles*128][slots]
-  int* ws_cnt;                     // [m_tiles*128][slots]   (-1 = overflow)
-  unsigned int* ws_idx;            // [m_tiles*128][slots][CAP]
-  float* ws_val;                   // [m_tiles*128][slots][CAP]
+  // one record per (latent, slot, column half): rec = (row * slots + slot) * 2 + half
+  float* ws_max;                   // [recs]       running maximum (scaled units)
+  int* ws_cnt;                     // [recs]       (-1 = overflow)
+  unsigned int* ws_idx;            // [recs][CAP]  chunk index = code / 32
+  float* ws_val;                   // [recs][CAP]  chunk maximum
   int* err;                        // device error word (pipeline timeout)
 };
 
@@ -123,6 +127,37 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+  uint32_t r[64];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+        "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+        "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+        "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
+        "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float max32(const float* v) {
+  float t[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) t[j] = fmaxf(v[j], v[j + 16]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) t[j] = fmaxf(t[j], t[j + 8]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) t[j] = fmaxf(t[j], t[j + 4]);
+  return fmaxf(fmaxf(t[0], t[2]), fmaxf(t[1], t[3]));
+}
 // shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -159,8 +194,8 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   unsigned char* a_base = smem;
   unsigned char* b_base = smem + MAX_KB * A_KB_BYTES;
   unsigned int* cand_idx = reinterpret_cast<unsigned int*>(b_base + STAGES * B_STAGE_BYTES);
-  float* cand_val = reinterpret_cast<float*>(cand_idx + BM * CAP);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cand_val + BM * CAP);
+  float* cand_val = reinterpret_cast<float*>(cand_idx + 2 * BM * CAP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cand_val + 2 * BM * CAP);
   // bars: full[4], empty[4], a_full, a_empty, tmem_full[2], tmem_empty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
@@ -175,7 +210,7 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
     mbar_init(A_FULL, 1); mbar_init(A_EMPTY, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(T_FULL(s), 1); mbar_init(T_EMPTY(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(T_FULL(s), 1); mbar_init(T_EMPTY(s), EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -245,11 +280,12 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       tc_commit(A_EMPTY);                       // latent tile no longer read
     }
   } else if (warp >= 4) {
-    // ================= epilogue: running max + candidate band per latent =================
-    const int q = warp - 4;                     // TMEM lane quarter == warp_id % 4
+    // ================= epilogue: running max + candidate chunk band per latent =================
+    const int q = warp & 3;                     // TMEM lane quarter == warp_id % 4
+    const int half = (warp - 4) >> 2;           // which 128-column half of the accumulator
     const int row = q * 32 + lane;
-    unsigned int* my_idx = cand_idx + row * CAP;
-    float* my_val = cand_val + row * CAP;
+    unsigned int* my_idx = cand_idx + (half * BM + row) * CAP;
+    float* my_val = cand_val + (half * BM + row) * CAP;
     int acc = 0;
     uint32_t acc_phase = 0;
     long long pair = pair_begin;
@@ -260,43 +296,36 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       float run = -INFINITY;
       int cnt = 0;
       bool overflow = false;
+      auto push = [&](unsigned int chunk, float val, float thr) {
+        if (cnt == CAP) {                       // drop records that fell out of the band
+          int keep = 0;
+          for (int i = 0; i < CAP; ++i) {
+            const float pv = my_val[i];
+            if (pv >= thr) { my_val[keep] = pv; my_idx[keep] = my_idx[i]; ++keep; }
+          }
+          cnt = keep;
+        }
+        if (cnt < CAP) { my_idx[cnt] = chunk; my_val[cnt] = val; ++cnt; }
+        else overflow = true;
+      };
       for (int c = s.c_begin; c < s.c_end; ++c) {
         mbar_wait(T_FULL(acc), acc_phase, p.err, 6);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * BN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
-          float v[32];
-          tmem_ld32(taddr + ch * 32, v);
-          float t16[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) t16[j] = fmaxf(v[j], v[j + 16]);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) t16[j] = fmaxf(t16[j], t16[j + 8]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) t16[j] = fmaxf(t16[j], t16[j + 4]);
-          const float cmax = fmaxf(fmaxf(t16[0], t16[2]), fmaxf(t16[1], t16[3]));
-          const bool hit = active && !overflow && (cmax >= run - TAU);
+        for (int it = 0; it < BN / 2 / 64; ++it) {
+          float v[64];
+          tmem_ld64(taddr + it * 64, v);
+          const float ca = max32(v), cb = max32(v + 32);
+          const float cm = fmaxf(ca, cb);
+          const bool hit = active && !overflow && (cm >= run - TAU);
           if (__any_sync(0xffffffffu, hit)) {
             if (hit) {
-              run = fmaxf(run, cmax);
+              run = fmaxf(run, cm);
               const float thr = run - TAU;
-              const unsigned int code0 = (unsigned int)c * BN + ch * 32;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (v[j] >= thr) {
-                  if (cnt == CAP) {             // drop entries that fell out of the band
-                    int keep = 0;
-                    for (int i = 0; i < CAP; ++i) {
-                      const float pv = my_val[i];
-                      if (pv >= thr) { my_val[keep] = pv; my_idx[keep] = my_idx[i]; ++keep; }
-                    }
-                    cnt = keep;
-                  }
-                  if (cnt < CAP) { my_idx[cnt] = code0 + j; my_val[cnt] = v[j]; ++cnt; }
-                  else overflow = true;
-                }
-              }
+              const unsigned int chunk0 = (unsigned int)c * (BN / 32) + half * (BN / 64) + it * 2;
+              if (ca >= thr) push(chunk0, ca, thr);
+              if (cb >= thr) push(chunk0 + 1, cb, thr);
             }
           }
         }
@@ -306,7 +335,7 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       // publish this segment's record
-      const long long o = ((long long)s.m * BM + row) * p.slots + s.slot;
+      const long long o = (((long long)s.m * BM + row) * p.slots + s.slot) * 2 + half;
       p.ws_max[o] = active ? run : -INFINITY;
       p.ws_cnt[o] = active ? (overflow ? -1 : cnt) : 0;
       for (int i = 0; i < cnt; ++i) { p.ws_idx[o * CAP + i] = my_idx[i]; p.ws_val[o * CAP + i] = my_val[i]; }
@@ -321,7 +350,7 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 }
 
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + MAX_KB * A_KB_BYTES + STAGES * B_STAGE_BYTES +
-                              BM * CAP * 8 + 16 * 8 + 16;
+                              2 * BM * CAP * 8 + 16 * 8 + 16;
 
 // ---------------------------------------------------------------- merge + exact re-score
 __device__ __forceinline__ unsigned int f_order(float f) {
@@ -332,18 +361,19 @@ __device__ __forceinline__ unsigned int f_order(float f) {
 __global__ void __launch_bounds__(256)
 vq_rescore_kernel(const Params p, const float* __restrict__ xn, const float* __restrict__ en,
                   long long* __restrict__ idx, int* __restrict__ ovf_count, int* __restrict__ ovf_rows) {
-  const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  __shared__ float xs[8][MAX_KB * BK];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
   if (row >= p.n) return;
   const int m = (int)(row / BM);
-  // slots used by latent tile m
+  // records of latent tile m: slots c0..c1, two column halves each
   const long long c0 = ((long long)m * p.code_tiles) / p.per_cta;
   const long long c1 = ((long long)(m + 1) * p.code_tiles - 1) / p.per_cta;
-  const int nslots = (int)(c1 - c0 + 1);
-  const long long base = row * p.slots;
+  const int nrec = (int)(c1 - c0 + 1) * 2;
+  const long long base = row * p.slots * 2;
   float gmax = -INFINITY;
   bool ovf = false;
-  for (int s = lane; s < nslots; s += 32) {
+  for (int s = lane; s < nrec; s += 32) {
     gmax = fmaxf(gmax, p.ws_max[base + s]);
     ovf |= p.ws_cnt[base + s] < 0;
   }
@@ -353,32 +383,44 @@ vq_rescore_kernel(const Params p, const float* __restrict__ xn, const float* __r
     return;
   }
   const float thr = gmax - TAU;
+  for (int c = lane; c < p.d; c += 32) xs[wib][c] = xn[row * p.d + c];
+  __syncwarp();
   unsigned long long best = 0ull;
-  const float* x = xn + row * p.d;
-  const int total = nslots * CAP;
+  const int total = nrec * CAP;
   for (int e0 = 0; e0 < total; e0 += 32) {
     const int e = e0 + lane;
     bool valid = false;
-    unsigned int code = 0;
+    unsigned int chunk = 0;
     if (e < total) {
       const int s = e / CAP, i = e % CAP;
       if (i < p.ws_cnt[base + s] && p.ws_val[(base + s) * CAP + i] >= thr) {
         valid = true;
-        code = p.ws_idx[(base + s) * CAP + i];
+        chunk = p.ws_idx[(base + s) * CAP + i];
       }
     }
     unsigned int mask = __ballot_sync(0xffffffffu, valid);
     while (mask) {
       const int src = __ffs(mask) - 1;
       mask &= mask - 1;
-      const unsigned int cand = __shfl_sync(0xffffffffu, code, src);
-      const float* ev = en + (long long)cand * p.d;
+      // each lane scores one of the 32 codes of the chunk: exact fp32, sequential over d
+      const unsigned int code = __shfl_sync(0xffffffffu, chunk, src) * 32u + lane;
+      const float4* ev = reinterpret_cast<const float4*>(en + (long long)code * p.d);
       float acc = 0.f;
-      for (int c = lane; c < p.d; c += 32) acc = fmaf(x[c], ev[c], acc);
-      acc = warp_sum(acc);
-      const unsigned long long key = ((unsigned long long)f_order(acc) << 32) | (0xFFFFFFFFu - cand);
+      for (int c4 = 0; c4 < p.d / 4; ++c4) {
+        const float4 w = ev[c4];
+        acc = fmaf(xs[wib][4 * c4 + 0], w.x, acc);
+        acc = fmaf(xs[wib][4 * c4 + 1], w.y, acc);
+        acc = fmaf(xs[wib][4 * c4 + 2], w.z, acc);
+        acc = fmaf(xs[wib][4 * c4 + 3], w.w, acc);
+      }
+      const unsigned long long key = ((unsigned long long)f_order(acc) << 32) | (0xFFFFFFFFu - code);
       best = key > best ? key : best;
     }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other > best ? other : best;
   }
   if (lane == 0) idx[row] = (long long)(0xFFFFFFFFu - (unsigned int)(best & 0xFFFFFFFFull));
 }
@@ -395,13 +437,23 @@ vq_fallback_kernel(const Params p, const float* __restrict__ xn, const float* __
     const long long row = ovf_rows[i];
     const float* x = xn + row * p.d;
     unsigned long long best = 0ull;
-    for (long long code = warp; code < p.k; code += 8) {
-      const float* ev = en + code * p.d;
+    for (long long code = threadIdx.x; code < p.k; code += 256) {
+      const float4* ev = reinterpret_cast<const float4*>(en + code * p.d);
       float acc = 0.f;
-      for (int c = lane; c < p.d; c += 32) acc = fmaf(x[c], ev[c], acc);
-      acc = warp_sum(acc);
+      for (int c4 = 0; c4 < p.d / 4; ++c4) {
+        const float4 w = ev[c4];
+        acc = fmaf(x[4 * c4 + 0], w.x, acc);
+        acc = fmaf(x[4 * c4 + 1], w.y, acc);
+        acc = fmaf(x[4 * c4 + 2], w.z, acc);
+        acc = fmaf(x[4 * c4 + 3], w.w, acc);
+      }
       const unsigned long long key = ((unsigned long long)f_order(acc) << 32) | (0xFFFFFFFFu - (unsigned int)code);
       best = key > best ? key : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
     }
     if (lane == 0) wbest[warp] = best;
     __syncthreads();
@@ -465,10 +517,11 @@ static Plan make_plan(long long n, long long k) {
   const size_t rows = (size_t)pl.m_tiles * BM;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t o = 0;
-  pl.off_max = o; o = al(o + rows * pl.slots * sizeof(float));
-  pl.off_cnt = o; o = al(o + rows * pl.slots * sizeof(int));
-  pl.off_idx = o; o = al(o + rows * pl.slots * CAP * sizeof(unsigned int));
-  pl.off_val = o; o = al(o + rows * pl.slots * CAP * sizeof(float));
+  const size_t recs = rows * pl.slots * 2;
+  pl.off_max = o; o = al(o + recs * sizeof(float));
+  pl.off_cnt = o; o = al(o + recs * sizeof(int));
+  pl.off_idx = o; o = al(o + recs * CAP * sizeof(unsigned int));
+  pl.off_val = o; o = al(o + recs * CAP * sizeof(float));
   pl.off_ovf = o; o = al(o + 256 + (size_t)n * sizeof(int));
   pl.total = o;
   return pl;

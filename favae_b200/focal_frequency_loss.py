@@ -16,7 +16,28 @@ from torch import nn
 
 from . import _lib
 
-__all__ = ['FocalFrequencyLoss']
+__all__ = ['FocalFrequencyLoss', 'expected_upstream_scale']
+
+
+import contextlib
+import threading
+
+_tls = threading.local()
+
+
+@contextlib.contextmanager
+def expected_upstream_scale(scale):
+    """Tell the loss that its result will be multiplied by ``scale`` before ``backward`` (the
+    feature-loss wrappers divide by the number of levels, losses/vqgan_losses.py:28,48).  The
+    forward kernel then writes gradients already multiplied by ``scale`` and the backward pass
+    stays a no-op instead of re-scaling both gradient maps in HBM.  Purely an optimisation: any
+    other upstream gradient is still handled exactly."""
+    prev = getattr(_tls, 'scale', 1.0)
+    _tls.scale = float(scale)
+    try:
+        yield
+    finally:
+        _tls.scale = prev
 
 
 class _FFLFunction(torch.autograd.Function):
@@ -31,7 +52,8 @@ class _FFLFunction(torch.autograd.Function):
         gt = torch.empty_like(target) if need_t else None
         dev = pred.device
         map_loss = torch.empty((max(maps, 1),), device=dev, dtype=torch.float32)
-        gscale = 2.0 * loss_weight / mean_count
+        expected = getattr(_tls, 'scale', 1.0)
+        gscale = 2.0 * loss_weight / mean_count * expected
         st = _lib.stream()
         if batch_matrix:
             map_max = torch.empty((max(maps, 1),), device=dev, dtype=torch.float32)
@@ -49,6 +71,7 @@ class _FFLFunction(torch.autograd.Function):
         _lib.call('favae_sum_scaled', _lib.ptr(map_loss), maps, loss_weight / mean_count, _lib.ptr(loss), st)
         ctx.gp, ctx.gt = gp, gt
         ctx.prev_scale = None
+        ctx.expected = expected
         return loss.reshape(())
 
     @staticmethod
@@ -57,6 +80,8 @@ class _FFLFunction(torch.autograd.Function):
         if gp is None and gt is None:
             return (None,) * 8
         go = go.detach().to(torch.float32).reshape(1).contiguous()
+        if ctx.expected != 1.0:
+            go = go / ctx.expected           # exactly 1.0 when the announced scale was applied
         if ctx.prev_scale is not None:
             # second backward through the same graph: undo the previous scale, work on copies
             s = go / ctx.prev_scale

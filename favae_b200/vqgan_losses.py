@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import torch
 
+from .focal_frequency_loss import expected_upstream_scale
 from .gaussian_blur import gaussian_blur_reflect
 
 __all__ = ['recon_ffl_loss', 'recon_ffl_features_loss', 'recon_sl_gaussian_features_loss']
@@ -19,11 +20,13 @@ def recon_ffl_features_loss(ffl, en_feat, de_feat, device):            # :18-30
     de_feat.reverse()
     loss = torch.zeros(1, device=device)
     losses = []
-    for i in range(len(en_feat)):
-        level = ffl(de_feat[i], en_feat[i])
-        loss = loss + level
-        losses.append(level)
-    loss = loss / len(en_feat)
+    inv = torch.tensor(1.0) / len(en_feat)          # the float32 factor `loss / len` applies
+    with expected_upstream_scale(float(inv)):
+        for i in range(len(en_feat)):
+            level = ffl(de_feat[i], en_feat[i])
+            loss = loss + level
+            losses.append(level)
+    loss = loss * inv.to(loss.device)
     return loss, losses
 
 
@@ -31,11 +34,13 @@ def recon_sl_gaussian_features_loss(ffl, gaussian_kernel, gaussian_sigma, en_fea
     de_feat.reverse()
     loss = torch.zeros(1, device=device)
     losses = []
-    for i in range(len(en_feat)):
-        e = gaussian_blur_reflect(en_feat[i], float(gaussian_sigma), gaussian_kernel)
-        d = gaussian_blur_reflect(de_feat[i], float(gaussian_sigma), gaussian_kernel)
-        level = ffl(d, e)
-        loss = loss + level
-        losses.append(level)
-    loss = loss / len(en_feat)
+    inv = torch.tensor(1.0) / len(en_feat)
+    with expected_upstream_scale(float(inv)):
+        for i in range(len(en_feat)):
+            e = gaussian_blur_reflect(en_feat[i], float(gaussian_sigma), gaussian_kernel)
+            d = gaussian_blur_reflect(de_feat[i], float(gaussian_sigma), gaussian_kernel)
+            level = ffl(d, e)
+            loss = loss + level
+            losses.append(level)
+    loss = loss * inv.to(loss.device)
     return loss, losses
