@@ -21,11 +21,10 @@ The two all-reduces of the reference (:419, :427) become ONE all-reduce of the f
 from __future__ import annotations
 
 import torch
-import torch.distributed as distributed
 import torch.nn.functional as F
 from torch import nn
 
-from . import _lib
+from . import _dist, _lib
 
 __all__ = ['VectorQuantize', 'CosineSimCodebook', 'EuclideanCodebook', 'l2norm', 'orthogonal_loss_fn']
 
@@ -182,7 +181,7 @@ class _CodebookBase(nn.Module):
                       _lib.stream())
             if self.use_ddp:
                 # one all-reduce of [bins | embed_sum] (reference: two, :419/:427 and :291/:295)
-                distributed.all_reduce(stats)
+                _dist.all_reduce_stats(stats)
             self._ema_update(en, stats)
         return out, idx, loss_sum
 
