@@ -77,3 +77,26 @@ def test_patch_reference_installs_alias():
     assert 'focal_frequency_loss' in done
     from focal_frequency_loss import FocalFrequencyLoss
     assert FocalFrequencyLoss is favae_b200.FocalFrequencyLoss
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/models'), reason='reference checkout not present')
+def test_patch_reference_swaps_the_reference_modules():
+    """In the authoring container: the unmodified reference model builds on top of the drop-ins."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, warnings; warnings.filterwarnings('ignore');"
+        "sys.path.insert(0, '/root/reference'); sys.path.insert(0, %r);"
+        "import favae_b200; done = favae_b200.patch_reference();"
+        "from models.vqgan_fcm import VQGANFCM;"
+        "m = VQGANFCM(1024, 256, ch_mult=(1,1,2,2,4), attn_resolutions=[16], use_cosine_sim=True,"
+        " use_l2_quantizer=True, use_gauss_resblock=True, kernel_size=9, dsl_init_sigma=3.0, device='cpu');"
+        "assert type(m.quantizer) is favae_b200.VectorQuantize;"
+        "assert m.encoder._gaussian_blur.__func__.__module__ == 'favae_b200.gaussian_blur';"
+        "assert m.decoder._gaussian_blur.__func__.__module__ == 'favae_b200.gaussian_blur';"
+        "keys = sorted(k for k in m.state_dict() if k.startswith('quantizer'));"
+        "assert keys == ['quantizer._codebook.cluster_size', 'quantizer._codebook.embed', 'quantizer._codebook.initted'], keys;"
+        "import losses.vqgan_losses as l; assert l.recon_ffl_features_loss.__module__ == 'favae_b200.vqgan_losses';"
+        "print('ok', done)" % ROOT)
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'ok' in r.stdout, r.stderr[-2000:]
