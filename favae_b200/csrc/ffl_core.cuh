@@ -37,7 +37,15 @@
 #define FAVAE_HOST_FLOAT2
 struct float2 { float x, y; };
 static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 #endif
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define FAVAE_RSQRT(x) rsqrtf(x)
+#else
+#define FAVAE_RSQRT(x) (1.0f / sqrtf(x))
 #endif
 
 namespace favae {
@@ -134,7 +142,8 @@ template <int N_, int C_, int MPC_, int THREADS_> struct FflCfg {
   static_assert(C == 1 || MPC == 1, "clusters hold a single map");
   static_assert(32 % TG == 0, "a 1-D FFT group must sit inside a warp");
   static constexpr size_t SMEM_BYTES =
-      sizeof(float2) * (size_t)(S_FLOAT2 + STG_FLOAT2) + sizeof(float) * (size_t)(4 * THREADS + 8 * MPC + 8 * C);
+      sizeof(float2) * (size_t)(S_FLOAT2 + STG_FLOAT2) + sizeof(float) * (size_t)(4 * THREADS + 8 * MPC + 8 * C) + sizeof(unsigned int) * (size_t)N;
+  static constexpr int IO_V4 = N / (4 * TG);       // float4 per thread and input row
 };
 
 // per-thread registers that live across FAVAE_SYNC points
@@ -180,18 +189,28 @@ template <class Cfg> FAVAE_HD void s_locate(int w, int slot_map, int& owner, int
 // f(A) from A^2 (already ortho-normalised)
 FAVAE_HD float spectrum_f(float a2, float alpha, int log_matrix) {
   float f;
-  if (alpha == 1.0f) f = sqrtf(a2);
+  if (alpha == 1.0f) f = a2 > 0.0f ? a2 * FAVAE_RSQRT(a2) : 0.0f;     // sqrt without the slow path
   else if (alpha == 2.0f) f = a2;
   else f = powf(sqrtf(a2), alpha);
   if (log_matrix) f = logf(f + 1.0f);
   return f;
 }
 
-// weight = clamp(nan_to_0(f / fmax), 0, 1)
-FAVAE_HD float spectrum_w(float f, float fmax) {
-  float w = f / fmax;
-  if (!(w == w)) w = 0.0f;
-  return fminf(fmaxf(w, 0.0f), 1.0f);
+// weight = clamp(nan_to_0(f / fmax), 0, 1) with inv = 1/fmax (0 when fmax == 0: the NaN -> 0 rule)
+FAVAE_HD float spectrum_inv(float fmax) { return fmax > 0.0f ? 1.0f / fmax : 0.0f; }
+FAVAE_HD float spectrum_w(float f, float inv) { return fminf(fmaxf(f * inv, 0.0f), 1.0f); }
+
+// packed S address of map column w: owner CTA in the top byte, float2 offset of row 0 below
+template <class Cfg> FAVAE_HD unsigned int s_pack(int w) {
+  int owner, off;
+  s_locate<Cfg>(w, 0, owner, off);
+  return ((unsigned int)owner << 24) | (unsigned int)off;
+}
+template <class Cfg> FAVAE_HD void s_lookup(const unsigned int* tab, int w, int slot_map, int& owner, int& off) {
+  constexpr int GPC = Cfg::HALF / Cfg::C;
+  const unsigned int e = tab[w];
+  owner = (int)(e >> 24);
+  off = (int)(e & 0xFFFFFFu) + slot_map * (GPC * 2 * Cfg::COLSTRIDE);
 }
 
 // ----------------------------------------------------------------------------------

@@ -10,6 +10,7 @@
 //   env.fbuf(cta)        float scratch: [0,2T) thread partials, [2T,4T) lane partials,
 //                        [4T, 4T+8*MPC) per-map results, then 8*C cluster slots
 //   env.cl(cta, owner)   float* to the cluster slots of CTA `owner`
+//   env.tab(cta)         N packed S addresses (s_pack), built by ffl_init_thread
 //   env.twiddle(j, n)    e^{-2 pi i j / n}
 #pragma once
 
@@ -24,7 +25,10 @@ FAVAE_HD void ffl_init_thread(Env& env) {
     const int t = tid % Cfg::TG;
 #pragma unroll
     for (int k1 = 0; k1 < Cfg::R1; ++k1) r.tw[k1] = env.twiddle(t * k1, Cfg::N);
+    unsigned int* tab = env.tab(cta);
+    for (int w = tid; w < Cfg::N; w += Cfg::THREADS) tab[w] = s_pack<Cfg>(w);
   });
+  env.sync_cta();
 }
 
 // One batch = MPC maps (C == 1) or one map shared by the C CTAs of a cluster.
@@ -45,24 +49,53 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
   });
 
   // ---------------- P1: packed row FFTs, global -> S ----------------
+  // Inputs are read as float4 (each thread IO_V4 vectors per row and tensor) and redistributed to
+  // the FFT's strided layout through the group's staging area.
+  constexpr int V4 = Cfg::IO_V4;
   for (int pass = 0; pass < PASSES; ++pass) {
     env.for_threads([&](int cta, int tid) {
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
       const int g = tid / TG, t = tid % TG, item = pass * NG + g;
       const int m = item / GPC, rp = cta * GPC + item % GPC;
       const long long map = map0 + m;
-      if (map < p.maps) {
-        const float* pa = p.pred + map * (long long)(N * N) + rp * N;
-        const float* ta = p.target + map * (long long)(N * N) + rp * N;
+      const bool live = map < p.maps;
+      const long long base = map * (long long)(N * N) + rp * N;
+      float4* stg4 = reinterpret_cast<float4*>(env.stg(cta) + g * STG);
 #pragma unroll
-        for (int e = 0; e < R1; ++e) {
-          const int c = idx_in<Cfg>(t, e);
-          r.v[e] = make_float2(pa[c] - ta[c], pa[HALF * N + c] - ta[HALF * N + c]);
+      for (int j = 0; j < V4; ++j) {
+        const int f = t + TG * j;                        // float4 index inside the row
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (live) {
+          const float4 pa = *reinterpret_cast<const float4*>(p.pred + base + 4 * f);
+          const float4 ta = *reinterpret_cast<const float4*>(p.target + base + 4 * f);
+          const float4 pb = *reinterpret_cast<const float4*>(p.pred + base + HALF * N + 4 * f);
+          const float4 tb = *reinterpret_cast<const float4*>(p.target + base + HALF * N + 4 * f);
+          a = make_float4(pa.x - ta.x, pa.y - ta.y, pa.z - ta.z, pa.w - ta.w);
+          b = make_float4(pb.x - tb.x, pb.y - tb.y, pb.z - tb.z, pb.w - tb.w);
         }
-      } else {
-#pragma unroll
-        for (int e = 0; e < R1; ++e) r.v[e] = make_float2(0.f, 0.f);
+        if constexpr (Cfg::R2 > 1) {                     // interleave (row r', row r'+N/2) pairs
+          stg4[2 * f] = make_float4(a.x, b.x, a.y, b.y);
+          stg4[2 * f + 1] = make_float4(a.z, b.z, a.w, b.w);
+        } else {                                         // one thread owns the whole row pair
+          r.v[4 * j + 0] = make_float2(a.x, b.x); r.v[4 * j + 1] = make_float2(a.y, b.y);
+          r.v[4 * j + 2] = make_float2(a.z, b.z); r.v[4 * j + 3] = make_float2(a.w, b.w);
+        }
       }
+    });
+    env.sync_warp();
+    env.for_threads([&](int cta, int tid) {
+      ThreadRegs<Cfg>& r = env.regs(cta, tid);
+      const int g = tid / TG, t = tid % TG;
+      if constexpr (Cfg::R2 > 1) {
+        const float2* stg = env.stg(cta) + g * STG;
+#pragma unroll
+        for (int e = 0; e < R1; ++e) r.v[e] = stg[idx_in<Cfg>(t, e)];
+      }
+    });
+    env.sync_warp();
+    env.for_threads([&](int cta, int tid) {
+      ThreadRegs<Cfg>& r = env.regs(cta, tid);
+      const int g = tid / TG, t = tid % TG;
       fwd_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
     });
     env.sync_warp();
@@ -70,11 +103,12 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
       const int g = tid / TG, t = tid % TG, item = pass * NG + g;
       const int m = item / GPC, rp = cta * GPC + item % GPC;
+      const unsigned int* tab = env.tab(cta);
       fwd_stage2<Cfg>(r, t, env.stg(cta) + g * STG);
 #pragma unroll
       for (int e = 0; e < R1; ++e) {
         int owner, off;
-        s_locate<Cfg>(idx_out<Cfg>(t, e), m, owner, off);
+        s_lookup<Cfg>(tab, idx_out<Cfg>(t, e), m, owner, off);
         env.S(cta, owner)[off + rp] = r.v[e];
       }
     });
@@ -92,14 +126,19 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       s_locate<Cfg>(v == 0 ? 0 : v, m, o0, off0);
       s_locate<Cfg>(v == 0 ? HALF : N - v, m, o1, off1);
       const float2* S = env.S(cta, cta);
+      if (v == 0) {                                      // packed real columns 0 and N/2
 #pragma unroll
-      for (int e = 0; e < R1 / 2; ++e) {
-        const int rr = idx_in<Cfg>(t, e);
-        const float2 zv = S[off0 + rr], zw = S[off1 + rr];
-        if (v == 0) {
+        for (int e = 0; e < R1 / 2; ++e) {
+          const int rr = idx_in<Cfg>(t, e);
+          const float2 zv = S[off0 + rr], zw = S[off1 + rr];
           r.v[e] = make_float2(zv.x, zw.x);
           r.v[e + R1 / 2] = make_float2(zv.y, zw.y);
-        } else {
+        }
+      } else {                                           // separate the two packed real rows
+#pragma unroll
+        for (int e = 0; e < R1 / 2; ++e) {
+          const int rr = idx_in<Cfg>(t, e);
+          const float2 zv = S[off0 + rr], zw = S[off1 + rr];
           r.v[e] = make_float2(0.5f * (zv.x + zw.x), 0.5f * (zv.y - zw.y));
           r.v[e + R1 / 2] = make_float2(0.5f * (zv.y + zw.y), 0.5f * (zw.x - zv.x));
         }
@@ -116,17 +155,24 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       s_locate<Cfg>(v == 0 ? HALF : N - v, m, o1, off1);
       float2* S = env.S(cta, cta);
       fwd_stage2<Cfg>(r, t, env.stg(cta) + g * STG);
+      // out-layout register e holds u = idx_out(t, e); u and u + N/2 sit PO_OUT registers apart
+      if (v != 0) {
+        float sum = 0.f, mx = r.mx;
+#pragma unroll
+        for (int e = 0; e < R1; ++e) {
+          const float2 z = r.v[e];
+          const float a2 = (z.x * z.x + z.y * z.y) * inv_nn;
+          const float f = spectrum_f(a2, p.alpha, p.log_matrix);
+          sum = fmaf(f, a2, sum);
+          mx = fmaxf(mx, f);
+        }
+        r.sum = fmaf(2.0f, sum, r.sum);
+        r.mx = mx;
+      }
 #pragma unroll
       for (int e = 0; e < R1; ++e) {
         const int u = idx_out<Cfg>(t, e);
-        const float2 z = r.v[e];
-        if (v != 0) {
-          const float a2 = (z.x * z.x + z.y * z.y) * inv_nn;
-          const float f = spectrum_f(a2, p.alpha, p.log_matrix);
-          r.sum += 2.0f * f * a2;
-          r.mx = fmaxf(r.mx, f);
-        }
-        S[(u < HALF) ? off0 + u : off1 + (u - HALF)] = z;
+        S[(u < HALF) ? off0 + u : off1 + (u - HALF)] = r.v[e];
       }
     });
     env.sync_warp();
@@ -184,8 +230,10 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       for (int i = 0; i < L; ++i) { s += fb[2 * T + m * TMAP + i]; mx = fmaxf(mx, fb[3 * T + m * TMAP + i]); }
       if (C == 1) {
         fb[4 * T + 2 * m] = s;
-        fb[4 * T + 2 * m + 1] = p.fmax_override ? p.fmax_override[0] : mx;
+        const float used = p.fmax_override ? p.fmax_override[0] : mx;
+        fb[4 * T + 2 * m + 1] = used;
         fb[4 * T + 2 * MPC + m] = mx;
+        fb[4 * T + 3 * MPC + m] = spectrum_inv(used);
       } else {
         for (int o = 0; o < C; ++o) {
           float* cl = env.cl(cta, o);
@@ -203,8 +251,10 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       float s = 0.f, mx = 0.f;
       for (int o = 0; o < C; ++o) { s += cl[2 * o]; mx = fmaxf(mx, cl[2 * o + 1]); }
       fb[4 * T] = s;
-      fb[4 * T + 1] = p.fmax_override ? p.fmax_override[0] : mx;
+      const float used = p.fmax_override ? p.fmax_override[0] : mx;
+      fb[4 * T + 1] = used;
       fb[4 * T + 2 * MPC] = mx;
+      fb[4 * T + 3 * MPC] = spectrum_inv(used);
     }
   });
   if (C > 1) env.sync_cta();
@@ -227,7 +277,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
     if (cta != 0) return;
     const float* fb = env.fbuf(cta);
     const int m = tid / TMAP;
-    const float fmx = fb[4 * T + 2 * m + 1];
+    const float finv = fb[4 * T + 3 * MPC + m];
     int o, off0, off1;
     s_locate<Cfg>(0, m, o, off0);
     s_locate<Cfg>(HALF, m, o, off1);
@@ -241,8 +291,8 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       const float2 dn = make_float2(0.5f * (a.y + b.y), 0.5f * (b.x - a.x));
       const float a0 = (d0.x * d0.x + d0.y * d0.y) * inv_nn;
       const float an = (dn.x * dn.x + dn.y * dn.y) * inv_nn;
-      const float w0 = spectrum_w(spectrum_f(a0, p.alpha, p.log_matrix), fmx);
-      const float wn = spectrum_w(spectrum_f(an, p.alpha, p.log_matrix), fmx);
+      const float w0 = spectrum_w(spectrum_f(a0, p.alpha, p.log_matrix), finv);
+      const float wn = spectrum_w(spectrum_f(an, p.alpha, p.log_matrix), finv);
       S[ia] = make_float2(w0 * d0.x - wn * dn.y, w0 * d0.y + wn * dn.x);
       if (ib != ia) S[ib] = make_float2(w0 * d0.x + wn * dn.y, wn * dn.x - w0 * d0.y);
     }
@@ -256,7 +306,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       const float* fb = env.fbuf(cta);
       const int g = tid / TG, t = tid % TG, item = pass * NG + g;
       const int m = item / GPC, v = cta * GPC + item % GPC;
-      const float fmx = fb[4 * T + 2 * m + 1];
+      const float finv = fb[4 * T + 3 * MPC + m];
       int o0, o1, off0, off1;
       s_locate<Cfg>(v == 0 ? 0 : v, m, o0, off0);
       s_locate<Cfg>(v == 0 ? HALF : N - v, m, o1, off1);
@@ -264,13 +314,16 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
 #pragma unroll
       for (int e = 0; e < R1; ++e) {
         const int u = idx_out<Cfg>(t, e);
-        float2 z = S[(u < HALF) ? off0 + u : off1 + (u - HALF)];
-        if (v != 0) {
+        r.v[e] = S[(u < HALF) ? off0 + u : off1 + (u - HALF)];
+      }
+      if (v != 0) {                                      // group 0 was weighted in place by P4
+#pragma unroll
+        for (int e = 0; e < R1; ++e) {
+          const float2 z = r.v[e];
           const float a2 = (z.x * z.x + z.y * z.y) * inv_nn;
-          const float w = spectrum_w(spectrum_f(a2, p.alpha, p.log_matrix), fmx);
-          z.x *= w; z.y *= w;
+          const float w = spectrum_w(spectrum_f(a2, p.alpha, p.log_matrix), finv);
+          r.v[e] = make_float2(z.x * w, z.y * w);
         }
-        r.v[e] = z;
       }
       inv_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
     });
@@ -284,14 +337,19 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       s_locate<Cfg>(v == 0 ? HALF : N - v, m, o1, off1);
       float2* S = env.S(cta, cta);
       inv_stage2<Cfg>(r, t, env.stg(cta) + g * STG);
+      if (v == 0) {
 #pragma unroll
-      for (int e = 0; e < R1 / 2; ++e) {
-        const int rr = idx_in<Cfg>(t, e);
-        const float2 a = r.v[e], b = r.v[e + R1 / 2];
-        if (v == 0) {
+        for (int e = 0; e < R1 / 2; ++e) {
+          const int rr = idx_in<Cfg>(t, e);
+          const float2 a = r.v[e], b = r.v[e + R1 / 2];
           S[off0 + rr] = make_float2(a.x, b.x);
           S[off1 + rr] = make_float2(a.y, b.y);
-        } else {
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < R1 / 2; ++e) {
+          const int rr = idx_in<Cfg>(t, e);
+          const float2 a = r.v[e], b = r.v[e + R1 / 2];
           S[off0 + rr] = make_float2(a.x - b.y, a.y + b.x);
           S[off1 + rr] = make_float2(a.x + b.y, b.x - a.y);
         }
@@ -307,10 +365,11 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
       const int g = tid / TG, t = tid % TG, item = pass * NG + g;
       const int m = item / GPC, rp = cta * GPC + item % GPC;
+      const unsigned int* tab = env.tab(cta);
 #pragma unroll
       for (int e = 0; e < R1; ++e) {
         int owner, off;
-        s_locate<Cfg>(idx_out<Cfg>(t, e), m, owner, off);
+        s_lookup<Cfg>(tab, idx_out<Cfg>(t, e), m, owner, off);
         r.v[e] = env.S(cta, owner)[off + rp];
       }
       inv_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
@@ -318,18 +377,50 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
     env.sync_warp();
     env.for_threads([&](int cta, int tid) {
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
+      const int g = tid / TG, t = tid % TG;
+      inv_stage2<Cfg>(r, t, env.stg(cta) + g * STG);
+    });
+    env.sync_warp();
+    // back to float4 rows through the staging area, scaled, stored as +grad / -grad
+    env.for_threads([&](int cta, int tid) {
+      ThreadRegs<Cfg>& r = env.regs(cta, tid);
+      const int g = tid / TG, t = tid % TG;
+      if constexpr (Cfg::R2 > 1) {
+        float2* stg = env.stg(cta) + g * STG;
+#pragma unroll
+        for (int e = 0; e < R1; ++e) stg[idx_in<Cfg>(t, e)] = r.v[e];
+      }
+    });
+    env.sync_warp();
+    env.for_threads([&](int cta, int tid) {
+      ThreadRegs<Cfg>& r = env.regs(cta, tid);
       const int g = tid / TG, t = tid % TG, item = pass * NG + g;
       const int m = item / GPC, rp = cta * GPC + item % GPC;
       const long long map = map0 + m;
-      inv_stage2<Cfg>(r, t, env.stg(cta) + g * STG);
       if (map < p.maps) {
         const long long base = map * (long long)(N * N) + rp * N;
+        const float4* stg4 = reinterpret_cast<const float4*>(env.stg(cta) + g * STG);
+        const float gs = p.grad_scale;
 #pragma unroll
-        for (int e = 0; e < R1; ++e) {
-          const int c = idx_in<Cfg>(t, e);
-          const float ga = r.v[e].x * p.grad_scale, gb = r.v[e].y * p.grad_scale;
-          if (p.grad_pred) { p.grad_pred[base + c] = ga; p.grad_pred[base + HALF * N + c] = gb; }
-          if (p.grad_target) { p.grad_target[base + c] = -ga; p.grad_target[base + HALF * N + c] = -gb; }
+        for (int j = 0; j < V4; ++j) {
+          const int f = t + TG * j;
+          float4 a, b;
+          if constexpr (Cfg::R2 > 1) {
+            const float4 lo = stg4[2 * f], hi = stg4[2 * f + 1];
+            a = make_float4(lo.x * gs, lo.z * gs, hi.x * gs, hi.z * gs);
+            b = make_float4(lo.y * gs, lo.w * gs, hi.y * gs, hi.w * gs);
+          } else {
+            a = make_float4(r.v[4 * j].x * gs, r.v[4 * j + 1].x * gs, r.v[4 * j + 2].x * gs, r.v[4 * j + 3].x * gs);
+            b = make_float4(r.v[4 * j].y * gs, r.v[4 * j + 1].y * gs, r.v[4 * j + 2].y * gs, r.v[4 * j + 3].y * gs);
+          }
+          if (p.grad_pred) {
+            *reinterpret_cast<float4*>(p.grad_pred + base + 4 * f) = a;
+            *reinterpret_cast<float4*>(p.grad_pred + base + HALF * N + 4 * f) = b;
+          }
+          if (p.grad_target) {
+            *reinterpret_cast<float4*>(p.grad_target + base + 4 * f) = make_float4(-a.x, -a.y, -a.z, -a.w);
+            *reinterpret_cast<float4*>(p.grad_target + base + HALF * N + 4 * f) = make_float4(-b.x, -b.y, -b.z, -b.w);
+          }
         }
       }
     });

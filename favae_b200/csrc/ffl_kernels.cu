@@ -3,6 +3,7 @@
 // memory (N = 256) owns a map from the first load to the gradient store: pred and target
 // are read once, both gradients written once, nothing else touches HBM.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ffl_configs.cuh"
@@ -17,6 +18,7 @@ template <class Cfg> struct DevEnv {
   float2* s_;
   float2* stg_;
   float* fb_;
+  unsigned int* tab_;
   int rank_;
 
   template <class F> __device__ __forceinline__ void for_threads(F f) { f(rank_, (int)threadIdx.x); }
@@ -33,6 +35,7 @@ template <class Cfg> struct DevEnv {
   }
   __device__ __forceinline__ float2* stg(int) { return stg_; }
   __device__ __forceinline__ float* fbuf(int) { return fb_; }
+  __device__ __forceinline__ unsigned int* tab(int) { return tab_; }
   __device__ __forceinline__ float* cl(int, int owner) {
     float* base = fb_ + 4 * Cfg::THREADS + 8 * Cfg::MPC;
     if constexpr (Cfg::C == 1) return base;
@@ -46,12 +49,14 @@ template <class Cfg> struct DevEnv {
 };
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS) ffl_kernel(const FflParams p) {
+__global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 256 && Cfg::SMEM_BYTES < 110 * 1024) ? 2 : 1)
+ffl_kernel(const FflParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevEnv<Cfg> env;
   env.s_ = reinterpret_cast<float2*>(smem_raw);
   env.stg_ = env.s_ + Cfg::S_FLOAT2;
   env.fb_ = reinterpret_cast<float*>(env.stg_ + Cfg::STG_FLOAT2);
+  env.tab_ = reinterpret_cast<unsigned int*>(env.fb_ + 4 * Cfg::THREADS + 8 * Cfg::MPC + 8 * Cfg::C);
   if constexpr (Cfg::C == 1) env.rank_ = 0;
   else env.rank_ = (int)cg::this_cluster().block_rank();
   ffl_init_thread<Cfg>(env);
@@ -69,13 +74,7 @@ template <class Cfg> static int launch_ffl(const FflParams& p, cudaStream_t stre
     configured = true;
   }
   const long long batches = (p.maps + Cfg::MPC - 1) / Cfg::MPC;
-  int per_sm = (int)(200 * 1024 / Cfg::SMEM_BYTES);
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm * Cfg::THREADS > 2048) per_sm = 2048 / Cfg::THREADS;
-  long long clusters = (long long)num_sms() * per_sm / Cfg::C;
-  if (clusters > batches) clusters = batches;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(clusters * Cfg::C));
   cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
@@ -86,6 +85,24 @@ template <class Cfg> static int launch_ffl(const FflParams& p, cudaStream_t stre
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // persistent grid: exactly the clusters that can be co-resident
+  static int resident = 0;
+  if (!resident) {
+    int per_sm = (int)(232448 / (Cfg::SMEM_BYTES + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm * Cfg::THREADS > 2048) per_sm = 2048 / Cfg::THREADS;
+    int guess = num_sms() * per_sm / Cfg::C;
+    if (Cfg::C > 1) {
+      cfg.gridDim = dim3((unsigned)(guess * Cfg::C));
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) guess = n;
+      else (void)cudaGetLastError();
+    }
+    resident = guess;
+  }
+  long long clusters = resident;
+  if (clusters > batches) clusters = batches;
+  cfg.gridDim = dim3((unsigned)(clusters * Cfg::C));
   FAVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
   return check_launch("ffl_kernel");
 }
@@ -106,6 +123,8 @@ int favae_ffl_forward(const float* pred, const float* target, int64_t maps, int 
   FAVAE_REQUIRE(pred && target && map_loss, "ffl_forward: null pointer");
   FAVAE_REQUIRE(favae_ffl_supported(h, w), "ffl_forward: maps must be square, side a power of two in [8,256]");
   FAVAE_REQUIRE(maps >= 0, "ffl_forward: negative map count");
+  FAVAE_REQUIRE((((uintptr_t)pred | (uintptr_t)target | (uintptr_t)grad_pred | (uintptr_t)grad_target) & 15) == 0,
+                "ffl_forward: tensors must be 16-byte aligned");
   if (maps == 0) return 0;
   FflParams p;
   p.pred = pred; p.target = target; p.grad_pred = grad_pred; p.grad_target = grad_target;
@@ -119,7 +138,11 @@ int favae_ffl_forward(const float* pred, const float* target, int64_t maps, int 
     case 32: return launch_ffl<FflCfg32>(p, s);
     case 64: return launch_ffl<FflCfg64>(p, s);
     case 128: return launch_ffl<FflCfg128>(p, s);
-    default: return launch_ffl<FflCfg256>(p, s);
+    default: {
+      // FAVAE_FFL256=c2 selects the 2-CTA-cluster variant (one map per SM pair, 1 CTA/SM)
+      static const bool c2 = [] { const char* e = getenv("FAVAE_FFL256"); return e && e[0] == 'c' && e[1] == '2'; }();
+      return c2 ? launch_ffl<FflCfg256>(p, s) : launch_ffl<FflCfg256c4>(p, s);
+    }
   }
 }
 }

@@ -9,8 +9,9 @@
 // similarity is bounded by (2u + u^2)|x||e| plus the fp32 accumulation error, < 1.1e-3, so the
 // true fp32 arg-max always lies within TAU = 2.5e-3 of the approximate maximum.  The epilogue
 // works on 32-code chunks: every chunk whose maximum falls inside that band is recorded, and all
-// 32 codes of a recorded chunk are re-scored with exact fp32 dot products (vq_rescore_kernel,
-// same accumulation order as favae_vq_search_exact); ties go to the lowest index.  Rows whose candidate list overflows (pathological ties, all-zero latents)
+// codes of a recorded chunk that were inside the band when it was recorded (a 32-bit mask) are
+// re-scored with exact fp32 dot products (vq_rescore_kernel, same accumulation order as
+// favae_vq_search_exact); ties go to the lowest index.  Rows whose candidate list overflows (pathological ties, all-zero latents)
 // are searched exhaustively in fp32 (vq_fallback_kernel).  The result contract is therefore the
 // same as favae_vq_search_exact.
 //
@@ -58,6 +59,7 @@ struct Params {
   float* ws_max;                   // [recs]       running maximum (scaled units)
   int* ws_cnt;                     // [recs]       (-1 = overflow)
   unsigned int* ws_idx;            // [recs][CAP]  chunk index = code / 32
+  unsigned int* ws_mask;           // [recs][CAP]  codes of the chunk inside the band when recorded
   float* ws_val;                   // [recs][CAP]  chunk maximum
   int* err;                        // device error word (pipeline timeout)
 };
@@ -158,6 +160,12 @@ __device__ __forceinline__ float max32(const float* v) {
   for (int j = 0; j < 4; ++j) t[j] = fmaxf(t[j], t[j + 4]);
   return fmaxf(fmaxf(t[0], t[2]), fmaxf(t[1], t[3]));
 }
+__device__ __forceinline__ unsigned int band_mask32(const float* v, float thr) {
+  unsigned int m = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) m |= (v[j] >= thr ? 1u : 0u) << j;
+  return m;
+}
 // shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -195,7 +203,8 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   unsigned char* b_base = smem + MAX_KB * A_KB_BYTES;
   unsigned int* cand_idx = reinterpret_cast<unsigned int*>(b_base + STAGES * B_STAGE_BYTES);
   float* cand_val = reinterpret_cast<float*>(cand_idx + 2 * BM * CAP);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cand_val + 2 * BM * CAP);
+  unsigned int* cand_mask = reinterpret_cast<unsigned int*>(cand_val + 2 * BM * CAP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cand_mask + 2 * BM * CAP);
   // bars: full[4], empty[4], a_full, a_empty, tmem_full[2], tmem_empty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
@@ -286,6 +295,7 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int row = q * 32 + lane;
     unsigned int* my_idx = cand_idx + (half * BM + row) * CAP;
     float* my_val = cand_val + (half * BM + row) * CAP;
+    unsigned int* my_mask = cand_mask + (half * BM + row) * CAP;
     int acc = 0;
     uint32_t acc_phase = 0;
     long long pair = pair_begin;
@@ -296,16 +306,16 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       float run = -INFINITY;
       int cnt = 0;
       bool overflow = false;
-      auto push = [&](unsigned int chunk, float val, float thr) {
+      auto push = [&](unsigned int chunk, float val, float thr, unsigned int mask) {
         if (cnt == CAP) {                       // drop records that fell out of the band
           int keep = 0;
           for (int i = 0; i < CAP; ++i) {
             const float pv = my_val[i];
-            if (pv >= thr) { my_val[keep] = pv; my_idx[keep] = my_idx[i]; ++keep; }
+            if (pv >= thr) { my_val[keep] = pv; my_idx[keep] = my_idx[i]; my_mask[keep] = my_mask[i]; ++keep; }
           }
           cnt = keep;
         }
-        if (cnt < CAP) { my_idx[cnt] = chunk; my_val[cnt] = val; ++cnt; }
+        if (cnt < CAP) { my_idx[cnt] = chunk; my_val[cnt] = val; my_mask[cnt] = mask; ++cnt; }
         else overflow = true;
       };
       for (int c = s.c_begin; c < s.c_end; ++c) {
@@ -324,8 +334,8 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               run = fmaxf(run, cm);
               const float thr = run - TAU;
               const unsigned int chunk0 = (unsigned int)c * (BN / 32) + half * (BN / 64) + it * 2;
-              if (ca >= thr) push(chunk0, ca, thr);
-              if (cb >= thr) push(chunk0 + 1, cb, thr);
+              if (ca >= thr) push(chunk0, ca, thr, band_mask32(v, thr));
+              if (cb >= thr) push(chunk0 + 1, cb, thr, band_mask32(v + 32, thr));
             }
           }
         }
@@ -338,7 +348,9 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const long long o = (((long long)s.m * BM + row) * p.slots + s.slot) * 2 + half;
       p.ws_max[o] = active ? run : -INFINITY;
       p.ws_cnt[o] = active ? (overflow ? -1 : cnt) : 0;
-      for (int i = 0; i < cnt; ++i) { p.ws_idx[o * CAP + i] = my_idx[i]; p.ws_val[o * CAP + i] = my_val[i]; }
+      for (int i = 0; i < cnt; ++i) {
+        p.ws_idx[o * CAP + i] = my_idx[i]; p.ws_val[o * CAP + i] = my_val[i]; p.ws_mask[o * CAP + i] = my_mask[i];
+      }
     }
   }
 
@@ -350,7 +362,7 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 }
 
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + MAX_KB * A_KB_BYTES + STAGES * B_STAGE_BYTES +
-                              2 * BM * CAP * 8 + 16 * 8 + 16;
+                              2 * BM * CAP * 12 + 16 * 8 + 16;
 
 // ---------------------------------------------------------------- merge + exact re-score
 __device__ __forceinline__ unsigned int f_order(float f) {
@@ -358,10 +370,13 @@ __device__ __forceinline__ unsigned int f_order(float f) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+constexpr int RESCORE_CAP = 96;      // candidate codes per latent handled in place; more -> fallback
+
 __global__ void __launch_bounds__(256)
 vq_rescore_kernel(const Params p, const float* __restrict__ xn, const float* __restrict__ en,
                   long long* __restrict__ idx, int* __restrict__ ovf_count, int* __restrict__ ovf_rows) {
   __shared__ float xs[8][MAX_KB * BK];
+  __shared__ unsigned int cand[8][RESCORE_CAP];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
   if (row >= p.n) return;
@@ -378,44 +393,59 @@ vq_rescore_kernel(const Params p, const float* __restrict__ xn, const float* __r
     ovf |= p.ws_cnt[base + s] < 0;
   }
   gmax = warp_max(gmax);
-  if (__any_sync(0xffffffffu, ovf)) {
+  ovf = __any_sync(0xffffffffu, ovf);           // warp-uniform from here on
+  const float thr = gmax - TAU;
+  // gather the candidate codes of all records still inside the band
+  int total = 0;
+  const int nent = nrec * CAP;
+  for (int e0 = 0; e0 < nent && !ovf; e0 += 32) {
+    const int e = e0 + lane;
+    unsigned int chunk = 0, mask = 0;
+    if (e < nent) {
+      const int s = e / CAP, i = e % CAP;
+      if (i < p.ws_cnt[base + s] && p.ws_val[(base + s) * CAP + i] >= thr) {
+        chunk = p.ws_idx[(base + s) * CAP + i];
+        mask = p.ws_mask[(base + s) * CAP + i];
+      }
+    }
+    const int mine = __popc(mask);
+    int incl = mine;                              // inclusive warp scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int pos = total + incl - mine;
+    total += __shfl_sync(0xffffffffu, incl, 31);
+    if (total > RESCORE_CAP) { ovf = true; break; }
+    while (mask) {
+      const int b = __ffs(mask) - 1;
+      mask &= mask - 1;
+      cand[wib][pos++] = chunk * 32u + b;
+    }
+  }
+  if (ovf) {
     if (lane == 0) ovf_rows[atomicAdd(ovf_count, 1)] = (int)row;
     return;
   }
-  const float thr = gmax - TAU;
   for (int c = lane; c < p.d; c += 32) xs[wib][c] = xn[row * p.d + c];
   __syncwarp();
+  // each lane scores one candidate: exact fp32, sequential over d (the order of the exact kernel)
   unsigned long long best = 0ull;
-  const int total = nrec * CAP;
-  for (int e0 = 0; e0 < total; e0 += 32) {
-    const int e = e0 + lane;
-    bool valid = false;
-    unsigned int chunk = 0;
-    if (e < total) {
-      const int s = e / CAP, i = e % CAP;
-      if (i < p.ws_cnt[base + s] && p.ws_val[(base + s) * CAP + i] >= thr) {
-        valid = true;
-        chunk = p.ws_idx[(base + s) * CAP + i];
-      }
+  for (int i = lane; i < total; i += 32) {
+    const unsigned int code = cand[wib][i];
+    const float4* ev = reinterpret_cast<const float4*>(en + (long long)code * p.d);
+    float acc = 0.f;
+#pragma unroll 4
+    for (int c4 = 0; c4 < p.d / 4; ++c4) {
+      const float4 w = ev[c4];
+      acc = fmaf(xs[wib][4 * c4 + 0], w.x, acc);
+      acc = fmaf(xs[wib][4 * c4 + 1], w.y, acc);
+      acc = fmaf(xs[wib][4 * c4 + 2], w.z, acc);
+      acc = fmaf(xs[wib][4 * c4 + 3], w.w, acc);
     }
-    unsigned int mask = __ballot_sync(0xffffffffu, valid);
-    while (mask) {
-      const int src = __ffs(mask) - 1;
-      mask &= mask - 1;
-      // each lane scores one of the 32 codes of the chunk: exact fp32, sequential over d
-      const unsigned int code = __shfl_sync(0xffffffffu, chunk, src) * 32u + lane;
-      const float4* ev = reinterpret_cast<const float4*>(en + (long long)code * p.d);
-      float acc = 0.f;
-      for (int c4 = 0; c4 < p.d / 4; ++c4) {
-        const float4 w = ev[c4];
-        acc = fmaf(xs[wib][4 * c4 + 0], w.x, acc);
-        acc = fmaf(xs[wib][4 * c4 + 1], w.y, acc);
-        acc = fmaf(xs[wib][4 * c4 + 2], w.z, acc);
-        acc = fmaf(xs[wib][4 * c4 + 3], w.w, acc);
-      }
-      const unsigned long long key = ((unsigned long long)f_order(acc) << 32) | (0xFFFFFFFFu - code);
-      best = key > best ? key : best;
-    }
+    const unsigned long long key = ((unsigned long long)f_order(acc) << 32) | (0xFFFFFFFFu - code);
+    best = key > best ? key : best;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -500,7 +530,7 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, int d, i
 struct Plan {
   int m_tiles, code_tiles, grid, slots;
   long long pairs, per_cta;
-  size_t off_max, off_cnt, off_idx, off_val, off_ovf, total;
+  size_t off_max, off_cnt, off_idx, off_mask, off_val, off_ovf, total;
 };
 
 static Plan make_plan(long long n, long long k) {
@@ -521,6 +551,7 @@ static Plan make_plan(long long n, long long k) {
   pl.off_max = o; o = al(o + recs * sizeof(float));
   pl.off_cnt = o; o = al(o + recs * sizeof(int));
   pl.off_idx = o; o = al(o + recs * CAP * sizeof(unsigned int));
+  pl.off_mask = o; o = al(o + recs * CAP * sizeof(unsigned int));
   pl.off_val = o; o = al(o + recs * CAP * sizeof(float));
   pl.off_ovf = o; o = al(o + 256 + (size_t)n * sizeof(int));
   pl.total = o;
@@ -567,6 +598,7 @@ int favae_vq_search_tc(const void* xh, const void* eh, const float* xn, const fl
   p.ws_max = (float*)(ws + pl.off_max);
   p.ws_cnt = (int*)(ws + pl.off_cnt);
   p.ws_idx = (unsigned int*)(ws + pl.off_idx);
+  p.ws_mask = (unsigned int*)(ws + pl.off_mask);
   p.ws_val = (float*)(ws + pl.off_val);
   int* ovf_count = (int*)(ws + pl.off_ovf);
   int* ovf_rows = ovf_count + 64;

@@ -140,5 +140,9 @@ class FocalFrequencyLoss(nn.Module):
             raise NotImplementedError(f'favae_b200: spectrum loss needs square power-of-two maps with side '
                                       f'in [8, 256], got {h}x{w}')
         p, t = p.contiguous(), t.contiguous()
+        if p.data_ptr() % 16:            # float4 access in the kernel
+            p = p.clone()
+        if t.data_ptr() % 16:
+            t = t.clone()
         return _FFLFunction.apply(p, t, float(self.loss_weight), float(self.alpha), bool(self.log_matrix),
                                   bool(self.batch_matrix), float(p.numel()), torch.is_grad_enabled())

@@ -14,10 +14,11 @@ template <class Cfg> struct HostEnv {
   std::vector<ThreadRegs<Cfg>> regs_;
   std::vector<float2> S_, stg_;
   std::vector<float> fb_;
+  std::vector<unsigned int> tab_;
   static constexpr int FB = 4 * Cfg::THREADS + 8 * Cfg::MPC + 8 * Cfg::C;
   HostEnv()
       : regs_(Cfg::C * Cfg::THREADS), S_((size_t)Cfg::C * Cfg::S_FLOAT2),
-        stg_((size_t)Cfg::C * Cfg::STG_FLOAT2), fb_((size_t)Cfg::C * FB) {
+        stg_((size_t)Cfg::C * (Cfg::STG_FLOAT2 + 2)), fb_((size_t)Cfg::C * FB), tab_((size_t)Cfg::C * Cfg::N) {
     // poison so that reads of never-written slots show up
     for (auto& z : S_) { z.x = NAN; z.y = NAN; }
     for (auto& z : stg_) { z.x = NAN; z.y = NAN; }
@@ -31,7 +32,8 @@ template <class Cfg> struct HostEnv {
   void sync_cluster() {}
   ThreadRegs<Cfg>& regs(int cta, int tid) { return regs_[cta * Cfg::THREADS + tid]; }
   float2* S(int, int owner) { return S_.data() + (size_t)owner * Cfg::S_FLOAT2; }
-  float2* stg(int cta) { return stg_.data() + (size_t)cta * Cfg::STG_FLOAT2; }
+  float2* stg(int cta) { return stg_.data() + (size_t)cta * (Cfg::STG_FLOAT2 + 2); }
+  unsigned int* tab(int cta) { return tab_.data() + (size_t)cta * Cfg::N; }
   float* fbuf(int cta) { return fb_.data() + (size_t)cta * FB; }
   float* cl(int, int owner) { return fbuf(owner) + 4 * Cfg::THREADS + 8 * Cfg::MPC; }
   float2 twiddle(int j, int n) {
@@ -61,6 +63,7 @@ extern "C" int ffl_emul(int n, const float* pred, const float* target, long long
     case 64: run<FflCfg64>(p); break;
     case 128: run<FflCfg128>(p); break;
     case 256: run<FflCfg256>(p); break;
+    case 2564: run<FflCfg256c4>(p); break;
     default: return -1;
   }
   return 0;

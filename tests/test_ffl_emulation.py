@@ -30,9 +30,10 @@ def emul():
 
 @pytest.mark.parametrize('n,maps,alpha,logm', [
     (8, 5, 1.0, 0), (8, 70, 1.0, 0), (16, 3, 1.0, 0), (16, 33, 1.0, 0), (32, 9, 1.0, 0),
-    (64, 2, 1.0, 0), (128, 1, 1.0, 0), (256, 1, 1.0, 0),
+    (64, 2, 1.0, 0), (128, 1, 1.0, 0), (256, 1, 1.0, 0), (2564, 1, 1.0, 0),
     (16, 4, 2.0, 0), (32, 4, 0.5, 0), (16, 4, 1.0, 1), (64, 1, 1.5, 1)])
 def test_emulated_kernel_matches_oracle(emul, n, maps, alpha, logm):
+    cfg, n = n, (256 if n == 2564 else n)       # 2564: the 4-CTA-cluster configuration of N = 256
     g = torch.Generator().manual_seed(n + maps)
     p = torch.randn(maps, 1, n, n, generator=g)
     t = torch.randn(maps, 1, n, n, generator=g)
@@ -40,7 +41,7 @@ def test_emulated_kernel_matches_oracle(emul, n, maps, alpha, logm):
     ml = torch.full((maps,), float('nan'))
     lw = 0.5
     gs = 2 * lw / p.numel() / (n * n)
-    assert emul.ffl_emul(n, p.data_ptr(), t.data_ptr(), maps, alpha, logm, gs,
+    assert emul.ffl_emul(cfg, p.data_ptr(), t.data_ptr(), maps, alpha, logm, gs,
                          gp.data_ptr(), gt.data_ptr(), ml.data_ptr(), None, None) == 0
     pd = p.double().requires_grad_(True); td = t.double().requires_grad_(True)
     ref = fo.focal_frequency_loss(pd, td, loss_weight=lw, alpha=alpha, log_matrix=bool(logm))
