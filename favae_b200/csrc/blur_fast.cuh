@@ -11,6 +11,7 @@
 //   MODE_ADJ_SIG  MODE_ADJ plus  d/dsigma <gy, H V x> = <(H'^T V^T + H^T V'^T) gy, x>  with
 //                 k' = dk/dsigma, sharing the single sliding window over gy (x is read once,
 //                 without halo)                                (autograd of vqgan_fcm.py:20-41)
+//   MODE_SIGMA    the same scalar as <gy, (H'V + HV') x>: forward data path on x, gy read once
 #pragma once
 
 #include "common.cuh"
@@ -19,7 +20,7 @@ namespace favae {
 namespace blurf {
 
 constexpr int THREADS = 128;
-constexpr int MODE_FWD = 0, MODE_ADJ = 1, MODE_ADJ_SIG = 2;
+constexpr int MODE_FWD = 0, MODE_ADJ = 1, MODE_ADJ_SIG = 2, MODE_SIGMA = 3;
 constexpr int LPAD = 8;                          // left halo slots of a shared line (>= p, 16B aligned)
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {
@@ -65,13 +66,15 @@ __device__ __forceinline__ void load_weights(const float* sigma_ptr, float* sk, 
 // border, which keeps its instruction stream as short as the forward one.
 
 template <int KS, int TH, int MODE>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, MODE == MODE_ADJ_SIG ? 4 : 1)
 blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ aux, int h, int w, long long items,
                  int strips, const float* __restrict__ sigma, float* __restrict__ dst,
                  float* __restrict__ partials) {
-  // src: x (FWD) or gy (ADJ*); aux: x (ADJ_SIG); dst: y / gx
+  // src: x (FWD, SIGMA) or gy (ADJ*); aux: x (ADJ_SIG) / gy (SIGMA); dst: y / gx
   constexpr int P = KS / 2;
-  constexpr bool ADJ = MODE != MODE_FWD, SIG = MODE == MODE_ADJ_SIG;
+  constexpr bool ADJ = MODE == MODE_ADJ || MODE == MODE_ADJ_SIG;
+  constexpr bool SIG = MODE == MODE_ADJ_SIG || MODE == MODE_SIGMA;
+  constexpr bool STORE = MODE != MODE_SIGMA;
   constexpr int NV = SIG ? 2 : 1;
   extern __shared__ float lines[];               // [2 buffers][groups][NV][w + 2*LPAD]
   __shared__ float sk[32], sdk[32];
@@ -117,7 +120,7 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ aux, i
   for (int q = 0; q < XQ; ++q) xq[q] = load_x(q);
   // FULL: all rows unrolled (fastest while the code fits the instruction cache: forward and plain
   // adjoint); otherwise RS-fold unroll inside a rolled loop (sigma-gradient variant)
-  constexpr bool FULL = !SIG;
+  constexpr bool FULL = MODE != MODE_ADJ_SIG;
   constexpr int STEP = FULL ? NR : RS;
 #pragma unroll 1
   for (int r0 = 0; r0 < NR; r0 += STEP) {
@@ -226,7 +229,7 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ aux, i
         }
       }
       if (live && yo < h) {
-        *reinterpret_cast<float4*>(dst + mapoff + (long long)yo * w + x0) = make_float4(o[0], o[1], o[2], o[3]);
+        if (STORE) *reinterpret_cast<float4*>(dst + mapoff + (long long)yo * w + x0) = make_float4(o[0], o[1], o[2], o[3]);
         if (SIG)
           acc_sigma = fmaf(xrow.x, z[0], fmaf(xrow.y, z[1], fmaf(xrow.z, z[2], fmaf(xrow.w, z[3], acc_sigma))));
       }
@@ -263,7 +266,7 @@ static int launch_one(const float* src, const float* aux, long long maps, int h,
   const int strips = (h + TH - 1) / TH, groups = THREADS / (w / 4);
   const long long items = maps * strips;
   const long long blocks = (items + groups - 1) / groups;
-  const size_t smem = sizeof(float) * 2 * groups * ((MODE == MODE_ADJ_SIG) ? 2 : 1) * (size_t)(w + 2 * LPAD);
+  const size_t smem = sizeof(float) * 2 * groups * ((MODE == MODE_ADJ_SIG || MODE == MODE_SIGMA) ? 2 : 1) * (size_t)(w + 2 * LPAD);
   blur_fast_kernel<KS, TH, MODE><<<(unsigned)blocks, THREADS, smem, s>>>(src, aux, h, w, items, strips, sigma, dst,
                                                                       partials);
   return check_launch("blur_fast");

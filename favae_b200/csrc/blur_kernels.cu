@@ -6,6 +6,8 @@
 // The reference builds the k x k outer product and runs a depthwise conv2d on the
 // reflect-padded map; the outer product of two identical 1-D Gaussians is applied here as
 // two 1-D passes over a shared-memory tile (same arithmetic up to fp32 rounding order).
+#include <stdlib.h>
+
 #include "blur_fast.cuh"
 #include "common.cuh"
 
@@ -259,7 +261,16 @@ int favae_blur_backward(const float* gy, const float* x, int64_t maps, int h, in
   }
   if (gx && blurf::supported(h, w, ksize) && aligned16(gy) && aligned16(gx) && (!gsigma || aligned16(x))) {
     if (!gsigma) return blurf::launch<blurf::MODE_ADJ>(gy, nullptr, maps, h, w, ksize, sigma, gx, nullptr, s);
-    rc = blurf::launch<blurf::MODE_ADJ_SIG>(gy, x, maps, h, w, ksize, sigma, gx, partials, s);
+    // one fused kernel (12 B/element).  FAVAE_BLUR_SIGMA=split runs the adjoint and a separate
+    // sigma-gradient kernel instead (16 B/element; measured 19 % slower in round 1, profiles/)
+    static const bool split = [] { const char* e = getenv("FAVAE_BLUR_SIGMA"); return e && e[0] == 's'; }();
+    if (!split) {
+      rc = blurf::launch<blurf::MODE_ADJ_SIG>(gy, x, maps, h, w, ksize, sigma, gx, partials, s);
+    } else {
+      rc = blurf::launch<blurf::MODE_ADJ>(gy, nullptr, maps, h, w, ksize, sigma, gx, nullptr, s);
+      if (rc) return rc;
+      rc = blurf::launch<blurf::MODE_SIGMA>(x, gy, maps, h, w, ksize, sigma, nullptr, partials, s);
+    }
     if (rc) return rc;
     return favae_sum_scaled(partials, blurf::num_blocks(maps, h, w), 1.0, gsigma, stream);
   }

@@ -139,9 +139,10 @@ int favae_ffl_forward(const float* pred, const float* target, int64_t maps, int 
     case 64: return launch_ffl<FflCfg64>(p, s);
     case 128: return launch_ffl<FflCfg128>(p, s);
     default: {
-      // FAVAE_FFL256=c2 selects the 2-CTA-cluster variant (one map per SM pair, 1 CTA/SM)
-      static const bool c2 = [] { const char* e = getenv("FAVAE_FFL256"); return e && e[0] == 'c' && e[1] == '2'; }();
-      return c2 ? launch_ffl<FflCfg256>(p, s) : launch_ffl<FflCfg256c4>(p, s);
+      // default: 2-CTA cluster, one map per SM pair.  FAVAE_FFL256=c4 selects the 4-CTA-cluster
+      // variant (two maps in flight per SM), measured 14 % slower in round 1 (profiles/)
+      static const bool c4 = [] { const char* e = getenv("FAVAE_FFL256"); return e && e[0] == 'c' && e[1] == '4'; }();
+      return c4 ? launch_ffl<FflCfg256c4>(p, s) : launch_ffl<FflCfg256>(p, s);
     }
   }
 }
