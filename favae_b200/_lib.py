@@ -28,6 +28,7 @@ SIGNATURES = {
     'favae_vq_search_exact': (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp]),
     'favae_vq_search_tc_workspace_bytes': (_sz, [_i64, _i64, _i32]),
     'favae_vq_search_tc': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _sz, _vp, _vp, _vp]),
+    'favae_vq_search_tc_overflow_rows': (_i32, [_vp, _i64, _i64, _i32, _vp]),
     'favae_vq_gather_st': (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
     'favae_vq_code_stats': (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp]),
     'favae_vq_ema_update_cosine': (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),

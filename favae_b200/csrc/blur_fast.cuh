@@ -66,7 +66,7 @@ __device__ __forceinline__ void load_weights(const float* sigma_ptr, float* sk, 
 // border, which keeps its instruction stream as short as the forward one.
 
 template <int KS, int TH, int MODE>
-__global__ void __launch_bounds__(THREADS, MODE == MODE_ADJ_SIG ? 4 : 1)
+__global__ void __launch_bounds__(THREADS)
 blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ aux, int h, int w, long long items,
                  int strips, const float* __restrict__ sigma, float* __restrict__ dst,
                  float* __restrict__ partials) {

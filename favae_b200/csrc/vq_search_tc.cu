@@ -15,6 +15,14 @@
 // are searched exhaustively in fp32 (vq_fallback_kernel).  The result contract is therefore the
 // same as favae_vq_search_exact.
 //
+// L2 traffic.  Streaming the codebook to every CTA needs 64 B/cycle/SM at full MMA rate -- more
+// than the ~6300 B/cycle the L2 can deliver to 148 SMs (measured: the single-CTA variant sits at
+// exactly that ceiling, 65 % tensor-active; TMA multicast inside a 2-CTA cluster does not reduce
+// L2 reads on this part).  The default variant therefore pairs two CTAs (cta_group::2): the pair
+// computes a 256-latent x 256-code tile, each CTA stages its own 128 latents and HALF of every
+// code block, the leader issues tcgen05.mma.cta_group::2 (M = 256) which reads both halves, and
+// each CTA's TMEM receives its own 128 rows.  L2 reads per MMA are halved.
+//
 // Work decomposition.  A work item is (128-latent tile m, 256-code tile c).  Items are
 // linearised m-major and cut into equal contiguous ranges, one per CTA (persistent, 1 CTA/SM),
 // so every SM is busy even when there are fewer latent tiles than SMs.  A CTA's range is a short
@@ -27,6 +35,7 @@
 // (TMA <-> MMA) and a double-buffered 2 x 256-column TMEM accumulator (MMA <-> epilogue).
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -48,12 +57,14 @@ constexpr uint32_t A_KB_BYTES = BM * BK * 2;        // 16 KB
 constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;     // 32 KB
 // instruction descriptor: D=f32 (bit 4), A=B=f16 K-major, N>>3 at bit 17, M>>4 at bit 24
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t IDESC2 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);  // M = 256
 
 struct Params {
   long long n, k;
   int d, kb;                       // kb = d / 64
   int m_tiles, code_tiles;
-  long long pairs, per_cta;
+  int mc;                          // 1: CTA pairs (cta_group::2), work unit = pair of latent tiles
+  long long pairs, per_cta;        // work items (m_unit, code tile) and items per CTA / cluster
   int slots;
   // one record per (latent, slot, column half): rec = (row * slots + slot) * 2 + half
   float* ws_max;                   // [recs]       running maximum (scaled units)
@@ -62,6 +73,7 @@ struct Params {
   unsigned int* ws_mask;           // [recs][CAP]  codes of the chunk inside the band when recorded
   float* ws_val;                   // [recs][CAP]  chunk maximum
   int* err;                        // device error word (pipeline timeout)
+  int debug;                       // profiling experiments only (FAVAE_VQ_TC_DEBUG): 1 = epilogue skips TMEM
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -101,6 +113,47 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;        // clears the CTA-rank bit: address in the pair's leader
+// 2-SM TMA load: data lands in THIS CTA's shared memory, the bytes are counted on the leader's barrier
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_mma_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC2), "r"(accumulate) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one elected lane of a converged warp (the role loops run warp-uniform so that descriptors and
+// barrier addresses stay in uniform registers; only the issue instructions are predicated)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -146,10 +199,10 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
         "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
         "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float max32(const float* v) {
   float t[16];
 #pragma unroll
@@ -179,91 +232,125 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 
 struct Segment { int m, c_begin, c_end, slot; };
 
-// segment `i` of this CTA's item range; returns false past the end
-__device__ __forceinline__ bool next_segment(const Params& p, long long& pair, long long end, Segment& s) {
+// next segment of this CTA's (cluster's) item range; returns false past the end.  s.m is the latent
+// tile of THIS CTA: with multicast the item's unit is a tile pair and rank picks the tile.
+__device__ __forceinline__ bool next_segment(const Params& p, long long unit_id, int rank, long long& pair,
+                                             long long end, Segment& s) {
   if (pair >= end) return false;
-  s.m = (int)(pair / p.code_tiles);
+  const int mu = (int)(pair / p.code_tiles);
+  s.m = p.mc ? 2 * mu + rank : mu;
   s.c_begin = (int)(pair % p.code_tiles);
   const long long left = end - pair;
   s.c_end = (int)min((long long)p.code_tiles, (long long)s.c_begin + left);
-  const long long first_cta = ((long long)s.m * p.code_tiles) / p.per_cta;
-  s.slot = (int)((long long)blockIdx.x - first_cta);
+  const long long first = ((long long)mu * p.code_tiles) / p.per_cta;
+  s.slot = (int)(unit_id - first);
   pair += s.c_end - s.c_begin;
   return true;
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const Params p) {
   extern __shared__ unsigned char smem_raw[];
   // 128-byte-swizzle tiles need 1024-byte alignment
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  // layout: A (MAX_KB x 16 KB) | B stages (4 x 32 KB) | candidate lists | barriers
+  // layout: A (MAX_KB x 16 KB) | B ring (128 KB: 4 x 32 KB, or 8 x 16 KB halves for CTA pairs) |
+  //         candidate lists | barriers
+  constexpr int NST = PAIR ? 2 * STAGES : STAGES;
+  constexpr uint32_t STB = PAIR ? B_STAGE_BYTES / 2 : B_STAGE_BYTES;
   unsigned char* a_base = smem;
   unsigned char* b_base = smem + MAX_KB * A_KB_BYTES;
   unsigned int* cand_idx = reinterpret_cast<unsigned int*>(b_base + STAGES * B_STAGE_BYTES);
   float* cand_val = reinterpret_cast<float*>(cand_idx + 2 * BM * CAP);
   unsigned int* cand_mask = reinterpret_cast<unsigned int*>(cand_val + 2 * BM * CAP);
   uint64_t* bars = reinterpret_cast<uint64_t*>(cand_mask + 2 * BM * CAP);
-  // bars: full[4], empty[4], a_full, a_empty, tmem_full[2], tmem_empty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  // bars: full[8], empty[8], a_full, a_empty, tmem_full[2], tmem_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
   auto FULL = [&](int s) { return bar0 + 8u * s; };
-  auto EMPTY = [&](int s) { return bar0 + 8u * (4 + s); };
-  const uint32_t A_FULL = bar0 + 8u * 8, A_EMPTY = bar0 + 8u * 9;
-  auto T_FULL = [&](int s) { return bar0 + 8u * (10 + s); };
-  auto T_EMPTY = [&](int s) { return bar0 + 8u * (12 + s); };
+  auto EMPTY = [&](int s) { return bar0 + 8u * (8 + s); };
+  const uint32_t A_FULL = bar0 + 8u * 16, A_EMPTY = bar0 + 8u * 17;
+  auto T_FULL = [&](int s) { return bar0 + 8u * (18 + s); };
+  auto T_EMPTY = [&](int s) { return bar0 + 8u * (20 + s); };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
     mbar_init(A_FULL, 1); mbar_init(A_EMPTY, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(T_FULL(s), 1); mbar_init(T_EMPTY(s), EPI_WARPS); }
+    // pair: the leader's tmem_empty collects the epilogue warps of both CTAs
+    for (int s = 0; s < 2; ++s) { mbar_init(T_FULL(s), 1); mbar_init(T_EMPTY(s), PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                 // both CTAs' barriers exist before anything is signalled
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const long long pair_begin = (long long)blockIdx.x * p.per_cta;
+  const int rank = PAIR ? (int)cluster_rank() : 0;
+  const bool leader = rank == 0;
+  const long long unit_id = PAIR ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long pair_begin = unit_id * p.per_cta;
   const long long pair_end = min(p.pairs, pair_begin + p.per_cta);
 
-  if (warp == 0 && lane == 0) {
-    // ================= TMA producer =================
+  if (warp == 0) {
+    // ================= TMA producer (warp-uniform loop, one elected lane issues) =================
     int stage = 0;
     uint32_t phase = 0, a_phase = 0;
     long long pair = pair_begin;
     Segment s;
-    while (next_segment(p, pair, pair_end, s)) {
+    while (next_segment(p, unit_id, rank, pair, pair_end, s)) {
       mbar_wait(A_EMPTY, a_phase ^ 1, p.err, 1);
-      mbar_expect_tx(A_FULL, (uint32_t)p.kb * A_KB_BYTES);
-      for (int kb = 0; kb < p.kb; ++kb)
-        tma_load_2d(smem_u32(a_base + kb * A_KB_BYTES), &map_a, A_FULL, kb * BK, s.m * BM);
+      if (elect_one()) {
+        if (PAIR) {
+          if (leader) mbar_expect_tx(A_FULL, 2u * (uint32_t)p.kb * A_KB_BYTES);   // both CTAs' latent tiles
+          for (int kb = 0; kb < p.kb; ++kb)
+            tma_load_2d_2sm(smem_u32(a_base + kb * A_KB_BYTES), &map_a, A_FULL, kb * BK, s.m * BM);
+        } else {
+          mbar_expect_tx(A_FULL, (uint32_t)p.kb * A_KB_BYTES);
+          for (int kb = 0; kb < p.kb; ++kb)
+            tma_load_2d(smem_u32(a_base + kb * A_KB_BYTES), &map_a, A_FULL, kb * BK, s.m * BM);
+        }
+      }
+      __syncwarp();
       a_phase ^= 1;
       for (int c = s.c_begin; c < s.c_end; ++c) {
         for (int kb = 0; kb < p.kb; ++kb) {
           mbar_wait(EMPTY(stage), phase ^ 1, p.err, 2);
-          mbar_expect_tx(FULL(stage), B_STAGE_BYTES);
-          tma_load_2d(smem_u32(b_base + stage * B_STAGE_BYTES), &map_b, FULL(stage), kb * BK, c * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (elect_one()) {
+            if (PAIR) {   // my half of the code block; the leader's barrier counts both halves
+              if (leader) mbar_expect_tx(FULL(stage), B_STAGE_BYTES);
+              tma_load_2d_2sm(smem_u32(b_base + stage * STB), &map_b, FULL(stage), kb * BK, c * BN + rank * (BN / 2));
+            } else {
+              mbar_expect_tx(FULL(stage), B_STAGE_BYTES);
+              tma_load_2d(smem_u32(b_base + stage * STB), &map_b, FULL(stage), kb * BK, c * BN);
+            }
+          }
+          __syncwarp();
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ================= MMA issuer =================
+  } else if (warp == 1 && leader) {
+    // ================= MMA issuer (the pair's leader issues for both CTAs) =================
     int stage = 0, acc = 0;
     uint32_t phase = 0, a_phase = 0, acc_phase = 0;
     long long pair = pair_begin;
     Segment s;
-    while (next_segment(p, pair, pair_end, s)) {
+    while (next_segment(p, unit_id, rank, pair, pair_end, s)) {
       mbar_wait(A_FULL, a_phase, p.err, 3);
       a_phase ^= 1;
       for (int c = s.c_begin; c < s.c_end; ++c) {
@@ -274,19 +361,31 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           mbar_wait(FULL(stage), phase, p.err, 5);
           tc_fence_after();
           const uint64_t da = make_desc(smem_u32(a_base + kb * A_KB_BYTES));
-          const uint64_t db = make_desc(smem_u32(b_base + stage * B_STAGE_BYTES));
+          const uint64_t db = make_desc(smem_u32(b_base + stage * STB));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            // advance both descriptors by k * 32 bytes inside the 128-byte swizzle row
-            tc_mma(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UK; ++k) {
+              // advance both descriptors by k * 32 bytes inside the 128-byte swizzle row
+              if (PAIR) tc_mma_2sm(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
+              else tc_mma(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), (kb | k) != 0 ? 1u : 0u);
+            }
+            if (PAIR) tc_commit_2sm(EMPTY(stage), (uint16_t)3);   // free the slot in both CTAs
+            else tc_commit(EMPTY(stage));         // smem slot free once these MMAs retire
+            if (kb == p.kb - 1) {                 // accumulator complete: wake the epilogue(s)
+              if (PAIR) tc_commit_2sm(T_FULL(acc), (uint16_t)3);
+              else tc_commit(T_FULL(acc));
+            }
           }
-          tc_commit(EMPTY(stage));              // smem slot free once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          __syncwarp();
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
-        tc_commit(T_FULL(acc));                 // accumulator ready for the epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      tc_commit(A_EMPTY);                       // latent tile no longer read
+      if (elect_one()) {
+        if (PAIR) tc_commit_2sm(A_EMPTY, (uint16_t)3);
+        else tc_commit(A_EMPTY);                // latent tile no longer read
+      }
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ================= epilogue: running max + candidate chunk band per latent =================
@@ -300,7 +399,7 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint32_t acc_phase = 0;
     long long pair = pair_begin;
     Segment s;
-    while (next_segment(p, pair, pair_end, s)) {
+    while (next_segment(p, unit_id, rank, pair, pair_end, s)) {
       const long long grow = (long long)s.m * BM + row;
       const bool active = grow < p.n;
       float run = -INFINITY;
@@ -322,11 +421,27 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         mbar_wait(T_FULL(acc), acc_phase, p.err, 6);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
-#pragma unroll 1
-        for (int it = 0; it < BN / 2 / 64; ++it) {
-          float v[64];
-          tmem_ld64(taddr + it * 64, v);
-          const float ca = max32(v), cb = max32(v + 32);
+        // pull this warp's 128 columns into registers and hand the accumulator back to the MMA
+        // pipe BEFORE scanning them: the drain time of a TMEM buffer is on the critical path of the
+        // two-buffer MMA <-> epilogue ring
+        float v[2][64];
+        if (p.debug & 1) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) { v[0][i] = -1.0e30f - 1.0e27f * (float)c - 1.0e24f * (float)i; v[1][i] = v[0][i] - 1.0e26f; }
+        } else {
+          tmem_ld64(taddr, v[0]);
+          tmem_ld64(taddr + 64, v[1]);
+          tmem_ld_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_remote(T_EMPTY(acc), 0);        // the leader's MMA thread waits on it
+          else mbar_arrive(T_EMPTY(acc));
+        }
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const float ca = max32(v[it]), cb = max32(v[it] + 32);
           const float cm = fmaxf(ca, cb);
           const bool hit = active && !overflow && (cm >= run - TAU);
           if (__any_sync(0xffffffffu, hit)) {
@@ -334,14 +449,11 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               run = fmaxf(run, cm);
               const float thr = run - TAU;
               const unsigned int chunk0 = (unsigned int)c * (BN / 32) + half * (BN / 64) + it * 2;
-              if (ca >= thr) push(chunk0, ca, thr, band_mask32(v, thr));
-              if (cb >= thr) push(chunk0 + 1, cb, thr, band_mask32(v + 32, thr));
+              if (ca >= thr) push(chunk0, ca, thr, band_mask32(v[it], thr));
+              if (cb >= thr) push(chunk0 + 1, cb, thr, band_mask32(v[it] + 32, thr));
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(T_EMPTY(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       // publish this segment's record
@@ -356,13 +468,15 @@ vq_search_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                 // no CTA leaves while the pair still uses its memory
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + MAX_KB * A_KB_BYTES + STAGES * B_STAGE_BYTES +
-                              2 * BM * CAP * 12 + 16 * 8 + 16;
+                              2 * BM * CAP * 12 + 24 * 8 + 16;
 
 // ---------------------------------------------------------------- merge + exact re-score
 __device__ __forceinline__ unsigned int f_order(float f) {
@@ -381,9 +495,10 @@ vq_rescore_kernel(const Params p, const float* __restrict__ xn, const float* __r
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
   if (row >= p.n) return;
   const int m = (int)(row / BM);
-  // records of latent tile m: slots c0..c1, two column halves each
-  const long long c0 = ((long long)m * p.code_tiles) / p.per_cta;
-  const long long c1 = ((long long)(m + 1) * p.code_tiles - 1) / p.per_cta;
+  const int mu = p.mc ? m >> 1 : m;                    // work unit (latent tile or tile pair)
+  // records of the unit: slots c0..c1, two column halves each
+  const long long c0 = ((long long)mu * p.code_tiles) / p.per_cta;
+  const long long c1 = ((long long)(mu + 1) * p.code_tiles - 1) / p.per_cta;
   const int nrec = (int)(c1 - c0 + 1) * 2;
   const long long base = row * p.slots * 2;
   float gmax = -INFINITY;
@@ -426,6 +541,11 @@ vq_rescore_kernel(const Params p, const float* __restrict__ xn, const float* __r
   }
   if (ovf) {
     if (lane == 0) ovf_rows[atomicAdd(ovf_count, 1)] = (int)row;
+    return;
+  }
+  __syncwarp();
+  if (total == 1) {                               // the common case: nothing to re-score
+    if (lane == 0) idx[row] = (long long)cand[wib][0];
     return;
   }
   for (int c = lane; c < p.d; c += 32) xs[wib][c] = xn[row * p.d + c];
@@ -528,23 +648,30 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, int d, i
 }
 
 struct Plan {
-  int m_tiles, code_tiles, grid, slots;
+  int m_tiles, code_tiles, grid, slots, mc;
   long long pairs, per_cta;
   size_t off_max, off_cnt, off_idx, off_mask, off_val, off_ovf, total;
 };
 
+static bool use_multicast() {
+  static const bool off = [] { const char* e = getenv("FAVAE_VQ_TC"); return e && e[0] == 'n'; }();
+  return !off;                                   // FAVAE_VQ_TC=nopair: single-CTA variant
+}
+
 static Plan make_plan(long long n, long long k) {
   Plan pl;
+  pl.mc = use_multicast() ? 1 : 0;
   pl.m_tiles = (int)((n + BM - 1) / BM);
   pl.code_tiles = (int)(k / BN);
-  pl.pairs = (long long)pl.m_tiles * pl.code_tiles;
-  long long g = num_sms();
+  const int units = pl.mc ? (pl.m_tiles + 1) / 2 : pl.m_tiles;
+  pl.pairs = (long long)units * pl.code_tiles;
+  long long g = pl.mc ? num_sms() / 2 : num_sms();          // clusters or CTAs
   if (g > pl.pairs) g = pl.pairs;
   if (g < 1) g = 1;
   pl.per_cta = (pl.pairs + g - 1) / g;
-  pl.grid = (int)((pl.pairs + pl.per_cta - 1) / pl.per_cta);
+  pl.grid = (int)((pl.pairs + pl.per_cta - 1) / pl.per_cta) * (pl.mc ? 2 : 1);
   pl.slots = (int)((pl.code_tiles + pl.per_cta - 1) / pl.per_cta) + 1;
-  const size_t rows = (size_t)pl.m_tiles * BM;
+  const size_t rows = (size_t)units * (pl.mc ? 2 : 1) * BM;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t o = 0;
   const size_t recs = rows * pl.slots * 2;
@@ -572,6 +699,14 @@ size_t favae_vq_search_tc_workspace_bytes(int64_t n, int64_t k, int d) {
   return tc::make_plan(n, k).total;
 }
 
+int favae_vq_search_tc_overflow_rows(const void* workspace, int64_t n, int64_t k, int d, int* count_host) {
+  FAVAE_REQUIRE(workspace && count_host && favae_vq_search_tc_workspace_bytes(n, k, d) > 0,
+                "vq_search_tc_overflow_rows: bad arguments");
+  const tc::Plan pl = tc::make_plan(n, k);
+  FAVAE_CUDA_OK(cudaMemcpy(count_host, (const unsigned char*)workspace + pl.off_ovf, sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int favae_vq_search_tc(const void* xh, const void* eh, const float* xn, const float* en, int64_t n,
                        int64_t k, int d, void* workspace, size_t workspace_bytes, uint64_t* keys,
                        int64_t* idx, void* stream) {
@@ -587,7 +722,7 @@ int favae_vq_search_tc(const void* xh, const void* eh, const float* xn, const fl
   CUtensorMap map_a, map_b;
   int rc = tc::make_map(&map_a, xh, n, d, tc::BM);
   if (rc) return rc;
-  rc = tc::make_map(&map_b, eh, k, d, tc::BN);
+  rc = tc::make_map(&map_b, eh, k, d, pl.mc ? tc::BN / 2 : tc::BN);   // CTA pair: each CTA loads half a block
   if (rc) return rc;
 
   unsigned char* ws = (unsigned char*)workspace;
@@ -605,13 +740,33 @@ int favae_vq_search_tc(const void* xh, const void* eh, const float* xn, const fl
   p.err = ovf_count + 1;
   FAVAE_CUDA_OK(cudaMemsetAsync(ovf_count, 0, 256, s));
 
+  p.mc = pl.mc;
+  { const char* e = getenv("FAVAE_VQ_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
   static bool configured = false;
   if (!configured) {
-    FAVAE_CUDA_OK(cudaFuncSetAttribute(tc::vq_search_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FAVAE_CUDA_OK(cudaFuncSetAttribute(tc::vq_search_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc::SMEM_BYTES));
+    FAVAE_CUDA_OK(cudaFuncSetAttribute(tc::vq_search_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)tc::SMEM_BYTES));
     configured = true;
   }
-  tc::vq_search_tc_kernel<<<pl.grid, tc::THREADS, tc::SMEM_BYTES, s>>>(map_a, map_b, p);
+  if (pl.mc) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)pl.grid);
+    cfg.blockDim = dim3(tc::THREADS);
+    cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FAVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, tc::vq_search_tc_kernel<true>, map_a, map_b, p));
+  } else {
+    tc::vq_search_tc_kernel<false><<<pl.grid, tc::THREADS, tc::SMEM_BYTES, s>>>(map_a, map_b, p);
+  }
   rc = check_launch("vq_search_tc");
   if (rc) return rc;
   tc::vq_rescore_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(p, xn, en, (long long*)idx, ovf_count, ovf_rows);

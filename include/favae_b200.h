@@ -66,6 +66,10 @@ int favae_vq_search_tc(const void* xh, const void* eh, const float* xn, const fl
                        int64_t n, int64_t k, int d, void* workspace, size_t workspace_bytes,
                        uint64_t* keys, int64_t* idx, void* stream);
 
+/* Diagnostics (synchronises): number of latents of the last favae_vq_search_tc call on this
+ * workspace that took the exhaustive fp32 fallback (candidate list overflow). */
+int favae_vq_search_tc_overflow_rows(const void* workspace, int64_t n, int64_t k, int d, int* count_host);
+
 /* Gather + straight-through + commitment-loss partial sums: replaces batched_embedding
  * (l2_quantize.py:166-170, :415), `x + (q - x).detach()` (:554) and the mse numerator (:560).
  * out has the layout of x.  loss_sum (1 float) receives sum((out - x)^2) (deterministic
