@@ -88,8 +88,11 @@ def main():
             ms = timed(lambda: _lib.call('favae_vq_search_tc', xh.data_ptr(), eh.data_ptr(), xn.data_ptr(),
                                          en.data_ptr(), n, K, D, ws.data_ptr(), nbytes, keys.data_ptr(),
                                          idx.data_ptr(), st()), it)
+            import ctypes
+            cnt = ctypes.c_int(-1)
+            _lib.call('favae_vq_search_tc_overflow_rows', ws.data_ptr(), n, K, D, ctypes.addressof(cnt))
             print(f'vq_search_tc n={n:7d}  {ms:8.3f} ms  {2.0 * n * K * D / ms / 1e9:8.1f} TFLOP/s algorithmic '
-                  f'(search + rescore + fallback)')
+                  f'(search + rescore + fallback; {cnt.value} latents took the exhaustive fallback)')
 
 
 if __name__ == '__main__':
