@@ -707,14 +707,6 @@ int favae_vq_search_tc_overflow_rows(const void* workspace, int64_t n, int64_t k
   return 0;
 }
 
-int favae_vq_search_tc_overflow_rows(const void* workspace, int64_t n, int64_t k, int d, int* count_host) {
-  FAVAE_REQUIRE(workspace && count_host && favae_vq_search_tc_workspace_bytes(n, k, d) > 0,
-                "vq_search_tc_overflow_rows: bad arguments");
-  const tc::Plan pl = tc::make_plan(n, k);
-  FAVAE_CUDA_OK(cudaMemcpy(count_host, (const unsigned char*)workspace + pl.off_ovf, sizeof(int), cudaMemcpyDeviceToHost));
-  return 0;
-}
-
 int favae_vq_search_tc(const void* xh, const void* eh, const float* xn, const float* en, int64_t n,
                        int64_t k, int d, void* workspace, size_t workspace_bytes, uint64_t* keys,
                        int64_t* idx, void* stream) {
