@@ -330,11 +330,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = args.batch * world * 1e3 / (float(t) / n_e2e)
 
-    # ---- VQ search alone (tensor-pipe roofline) on the step's latents
+    # ---- kernel-level rooflines measured alone (burst peaks): VQ search, level-0 blur
     n_lat = args.batch * 256
-    vq_ms = time_vq_search(hp, inp, device)
-    vq_flops = 2.0 * n_lat * K_CODES * DIM
-    vq_bytes = 4.0 * (n_lat * DIM + K_CODES * DIM) + 8.0 * n_lat
+    vq_ms = time_vq_search(n_lat, device)
+    big_n = 262144
+    vq_big_ms = time_vq_search(big_n, device)
+    blur_ms = time_blur(args.batch, device)
+
+    def vq_line(n, ms):
+        flops = 2.0 * n * K_CODES * DIM
+        return {'n_latents': n, 'ms_per_call': ms, 'achieved': flops / (ms * 1e-3) / 1e12,
+                'frac': flops / (ms * 1e-3) / 1e12 / pk['tf'],
+                'hbm_bound_ms': (4.0 * (n * DIM + K_CODES * DIM) + 8.0 * n) / (pk['hbm'] * 1e9) * 1e3}
 
     if rank == 0:
         e_l0 = args.batch * 128 * 256 * 256
@@ -347,13 +354,23 @@ def main():
             'clocks': clocks,
             'roofline': {'kernel': 'ffl_kernel<256> (level-0 DSL spectrum loss, 128x256x256 maps per image)',
                          'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm'], 'unit': 'GB/s',
-                         'frac': achieved / pk['hbm'], 'traffic': None, 'peak_source': pk['src'],
+                         'frac': achieved / pk['hbm'], 'traffic': 15.22 * e_l0, 'peak_source': pk['src'],
+                         'traffic_source': 'ncu --set full dram__bytes_read+write = 15.22 B/element (profiles/ncu_r1_summary.md)',
                          'algorithmic_bytes_per_launch': 16.0 * e_l0, 'ms_per_launch': l0_ms},
-            'roofline_vq': {'kernel': 'VQ nearest-code search (prepare + search)', 'bound': 'tensor',
-                            'achieved': vq_flops / (vq_ms * 1e-3) / 1e12, 'peak': pk['tf'], 'unit': 'TFLOP/s',
-                            'frac': vq_flops / (vq_ms * 1e-3) / 1e12 / pk['tf'],
-                            'hbm_bound_ms': vq_bytes / (pk['hbm'] * 1e9) * 1e3, 'ms_per_call': vq_ms,
-                            'n_latents': n_lat, 'codes': K_CODES, 'search_mode': os.environ.get('FAVAE_VQ_SEARCH', 'auto')},
+            'roofline_vq': {'kernel': 'favae_vq_search_tc: tcgen05 cta_group::2 search + exact re-score + fallback, '
+                                      '16384 x 256 codebook; algorithmic 2*N*K*D flops',
+                            'bound': 'tensor', 'peak': pk['tf'], 'unit': 'TFLOP/s', 'peak_source': pk['src'],
+                            'workload': vq_line(n_lat, vq_ms), 'microbench_large_n': vq_line(big_n, vq_big_ms),
+                            'achieved': vq_line(big_n, vq_big_ms)['achieved'], 'frac': vq_line(big_n, vq_big_ms)['frac']},
+            'roofline_blur': {'kernel': 'blur_fast_kernel<9,32,*> on the level-0 maps', 'bound': 'hbm',
+                              'peak': pk['hbm'], 'unit': 'GB/s',
+                              'forward': {'ms': blur_ms['fwd'], 'achieved': 8.0 * e_l0 / (blur_ms['fwd'] * 1e-3) / 1e9,
+                                          'frac': 8.0 * e_l0 / (blur_ms['fwd'] * 1e-3) / 1e9 / pk['hbm'],
+                                          'algorithmic_bytes_per_element': 8},
+                              'backward_with_sigma': {'ms': blur_ms['bwd'],
+                                                      'achieved': 12.0 * e_l0 / (blur_ms['bwd'] * 1e-3) / 1e9,
+                                                      'frac': 12.0 * e_l0 / (blur_ms['bwd'] * 1e-3) / 1e9 / pk['hbm'],
+                                                      'algorithmic_bytes_per_element': 12}},
             'cpu_baseline': cpu,
         })
         print(json.dumps(line), flush=True)
@@ -361,21 +378,63 @@ def main():
         dist.destroy_process_group()
 
 
-def time_vq_search(hp, inp, device, iters=5):
-    """Device time of one eval-mode quantizer call minus nothing: prepare + search + gather."""
-    hp.vq.eval()
-    with torch.no_grad():
+def time_vq_search(n_lat, device, iters=5):
+    """Device time of favae_vq_search_tc (tensor-core search + exact re-score + fallback) on n_lat
+    synthetic latents against a 16384 x 256 codebook, inputs prepared once."""
+    from favae_b200 import _lib
+    x = torch.randn(n_lat, DIM, device=device)
+    e = torch.nn.functional.normalize(torch.randn(K_CODES, DIM, device=device), dim=-1)
+    xn = torch.empty(n_lat, DIM, device=device); xh = torch.empty(n_lat, DIM, device=device, dtype=torch.float16)
+    en = torch.empty(K_CODES, DIM, device=device); eh = torch.empty(K_CODES, DIM, device=device, dtype=torch.float16)
+    st = _lib.stream()
+    _lib.call('favae_vq_prepare_rows', x.data_ptr(), n_lat, DIM, 1, 1, xn.data_ptr(), xh.data_ptr(), None, st)
+    _lib.call('favae_vq_prepare_rows', e.data_ptr(), K_CODES, DIM, 1, 1, en.data_ptr(), eh.data_ptr(), None, st)
+    nbytes = _lib.load().favae_vq_search_tc_workspace_bytes(n_lat, K_CODES, DIM)
+    ws = torch.empty(nbytes, device=device, dtype=torch.uint8)
+    idx = torch.empty(n_lat, device=device, dtype=torch.int64)
+    keys = torch.empty(n_lat, device=device, dtype=torch.int64)
+
+    def run():
+        _lib.call('favae_vq_search_tc', xh.data_ptr(), eh.data_ptr(), xn.data_ptr(), en.data_ptr(), n_lat, K_CODES,
+                  DIM, ws.data_ptr(), nbytes, keys.data_ptr(), idx.data_ptr(), _lib.stream())
+    for _ in range(3):
+        run()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(iters):
+        run()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def time_blur(batch, device, iters=5):
+    """Device time of the level-0 blur forward and backward (+ sigma gradient) kernels."""
+    from favae_b200 import _lib
+    shape = (batch, 128, 256, 256)
+    x = torch.randn(shape, device=device); g = torch.randn(shape, device=device)
+    y = torch.empty_like(x); gs = torch.empty(1, device=device)
+    sig = torch.tensor(SIGMA0, device=device)
+    maps = batch * 128
+    parts = torch.empty(int(_lib.load().favae_blur_partials(maps, 256, 256)), device=device)
+    out = {}
+    for name, fn in (
+            ('fwd', lambda: _lib.call('favae_blur_forward', x.data_ptr(), maps, 256, 256, KSIZE, sig.data_ptr(),
+                                      y.data_ptr(), _lib.stream())),
+            ('bwd', lambda: _lib.call('favae_blur_backward', g.data_ptr(), x.data_ptr(), maps, 256, 256, KSIZE,
+                                      sig.data_ptr(), y.data_ptr(), gs.data_ptr(), parts.data_ptr(), _lib.stream()))):
         for _ in range(2):
-            hp.vq(inp['z'])
+            fn()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         a.record()
         for _ in range(iters):
-            hp.vq(inp['z'])
+            fn()
         b.record()
         torch.cuda.synchronize()
-    hp.vq.train()
-    return a.elapsed_time(b) / iters
+        out[name] = a.elapsed_time(b) / iters
+    return out
 
 
 if __name__ == '__main__':
