@@ -73,6 +73,23 @@ def main():
         ms = timed(lambda: _lib.call('favae_blur_backward', t.data_ptr(), p.data_ptr(), B * 128, 256, 256, 9,
                                      sig.data_ptr(), gp.data_ptr(), None, None, st()), it)
         print(f'blur bwd k9        {ms:8.3f} ms  {8 * E / ms / 1e6:8.1f} GB/s (8 B/elem)')
+    if want('small'):
+        # the three 16 x 16 feature levels of the f=16 model: B*512, B*512, B*256 maps
+        for ch in (512, 256):
+            maps = B * ch
+            xs = torch.randn(maps, 16, 16, device=dev); gs_ = torch.randn(maps, 16, 16, device=dev)
+            ys = torch.empty_like(xs); sg = torch.tensor(3.0, device=dev); g1 = torch.empty(1, device=dev)
+            parts = torch.empty(int(_lib.load().favae_blur_partials(maps, 16, 16)), device=dev)
+            ml = torch.empty(maps, device=dev); gp2 = torch.empty_like(xs); gt2 = torch.empty_like(xs)
+            ms = timed(lambda: _lib.call('favae_blur_forward', xs.data_ptr(), maps, 16, 16, 9, sg.data_ptr(),
+                                         ys.data_ptr(), st()), it)
+            print(f'blur16 fwd  maps={maps:6d} {ms * 1e3:8.1f} us')
+            ms = timed(lambda: _lib.call('favae_blur_backward', gs_.data_ptr(), xs.data_ptr(), maps, 16, 16, 9,
+                                         sg.data_ptr(), ys.data_ptr(), g1.data_ptr(), parts.data_ptr(), st()), it)
+            print(f'blur16 bwd+sigma maps={maps:6d} {ms * 1e3:8.1f} us')
+            ms = timed(lambda: _lib.call('favae_ffl_forward', xs.data_ptr(), gs_.data_ptr(), maps, 16, 16, 1.0, 0,
+                                         1e-3, ml.data_ptr(), gp2.data_ptr(), gt2.data_ptr(), None, None, st()), it)
+            print(f'ffl16 fwd+grad maps={maps:6d} {ms * 1e3:8.1f} us')
     if want('vq'):
         K, D = 16384, 256
         for n in ([args.n_lat] if args.n_lat else [B * 256, 8192, 65536, 262144]):
