@@ -144,6 +144,10 @@ template <int N_, int C_, int MPC_, int THREADS_> struct FflCfg {
   static constexpr size_t SMEM_BYTES =
       sizeof(float2) * (size_t)(S_FLOAT2 + STG_FLOAT2) + sizeof(float) * (size_t)(4 * THREADS + 8 * MPC + 8 * C) + sizeof(unsigned int) * (size_t)N;
   static constexpr int IO_V4 = N / (4 * TG);       // float4 per thread and input row
+  // I/O staging of a row pair (N float2): elements with (c % 4) < 2 in [0, N/2), the others from
+  // IO_B2 on; the 8-slot shift keeps the strided float2 reads of the two halves on different banks
+  static constexpr int IO_B2 = N / 2 + 8;
+  static_assert(R2 == 1 || N + 8 <= R1 * STG_STRIDE, "I/O staging must fit the FFT staging area");
 };
 
 // per-thread registers that live across FAVAE_SYNC points
@@ -167,6 +171,11 @@ struct FflParams {
   float alpha;
   int log_matrix;
 };
+
+// float2 slot of row-pair element c in the I/O staging layout
+template <class Cfg> FAVAE_HD int io_slot(int c) {
+  return ((c & 2) ? Cfg::IO_B2 : 0) + 2 * (c >> 2) + (c & 1);
+}
 
 // out-layout / in-layout index of register e of lane t
 template <class Cfg> FAVAE_HD int idx_in(int t, int e) { return Cfg::R2 * e + t; }

@@ -3,7 +3,7 @@
 // `Env` abstracts the execution model so that the same phases run as a CUDA thread
 // block / cluster (ffl_kernels.cu) and as plain loops on the host (tests/emul):
 //   env.for_threads(f)   f(cta, tid) for every thread of every CTA of the cluster
-//   env.sync_warp/cta/cluster()
+//   env.sync_warp/cta/cluster()   env.cluster_arrive() / env.cluster_wait(): split cluster barrier
 //   env.regs(cta, tid)   ThreadRegs that persist across sync points
 //   env.S(cta, owner)    float2* to the spectrum buffer of CTA `owner` as seen from `cta`
 //   env.stg(cta)         staging for the two-stage 1-D FFT exchange
@@ -52,6 +52,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
   // Inputs are read as float4 (each thread IO_V4 vectors per row and tensor) and redistributed to
   // the FFT's strided layout through the group's staging area.
   constexpr int V4 = Cfg::IO_V4;
+  constexpr int IOB4 = Cfg::IO_B2 / 2;          // float4 index of the second half of the I/O staging
   for (int pass = 0; pass < PASSES; ++pass) {
     env.for_threads([&](int cta, int tid) {
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
@@ -74,8 +75,8 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
           b = make_float4(pb.x - tb.x, pb.y - tb.y, pb.z - tb.z, pb.w - tb.w);
         }
         if constexpr (Cfg::R2 > 1) {                     // interleave (row r', row r'+N/2) pairs
-          stg4[2 * f] = make_float4(a.x, b.x, a.y, b.y);
-          stg4[2 * f + 1] = make_float4(a.z, b.z, a.w, b.w);
+          stg4[f] = make_float4(a.x, b.x, a.y, b.y);          // elements 4f, 4f+1
+          stg4[IOB4 + f] = make_float4(a.z, b.z, a.w, b.w);   // elements 4f+2, 4f+3 (bank-shifted half)
         } else {                                         // one thread owns the whole row pair
           r.v[4 * j + 0] = make_float2(a.x, b.x); r.v[4 * j + 1] = make_float2(a.y, b.y);
           r.v[4 * j + 2] = make_float2(a.z, b.z); r.v[4 * j + 3] = make_float2(a.w, b.w);
@@ -89,7 +90,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       if constexpr (Cfg::R2 > 1) {
         const float2* stg = env.stg(cta) + g * STG;
 #pragma unroll
-        for (int e = 0; e < R1; ++e) r.v[e] = stg[idx_in<Cfg>(t, e)];
+        for (int e = 0; e < R1; ++e) r.v[e] = stg[io_slot<Cfg>(idx_in<Cfg>(t, e))];
       }
     });
     env.sync_warp();
@@ -105,6 +106,10 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       const int m = item / GPC, rp = cta * GPC + item % GPC;
       const unsigned int* tab = env.tab(cta);
       fwd_stage2<Cfg>(r, t, env.stg(cta) + g * STG);
+      // the previous map's P6 reads of S (arrived at the end of the last batch) must be complete
+      // before anybody overwrites S: the wait half of the split barrier sits here, after this
+      // map's loads and row FFTs
+      if (pass == 0) env.cluster_wait();
 #pragma unroll
       for (int e = 0; e < R1; ++e) {
         int owner, off;
@@ -268,7 +273,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
     }
   });
   if (p.grad_pred == nullptr && p.grad_target == nullptr) {
-    env.sync_cluster();
+    env.for_threads([&](int, int) { env.cluster_arrive(); });     // S is not read again
     return;
   }
 
@@ -372,6 +377,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
         s_lookup<Cfg>(tab, idx_out<Cfg>(t, e), m, owner, off);
         r.v[e] = env.S(cta, owner)[off + rp];
       }
+      if (pass == PASSES - 1) env.cluster_arrive();      // last read of S: release it for the next map
       inv_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
     });
     env.sync_warp();
@@ -388,7 +394,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       if constexpr (Cfg::R2 > 1) {
         float2* stg = env.stg(cta) + g * STG;
 #pragma unroll
-        for (int e = 0; e < R1; ++e) stg[idx_in<Cfg>(t, e)] = r.v[e];
+        for (int e = 0; e < R1; ++e) stg[io_slot<Cfg>(idx_in<Cfg>(t, e))] = r.v[e];
       }
     });
     env.sync_warp();
@@ -406,7 +412,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
           const int f = t + TG * j;
           float4 a, b;
           if constexpr (Cfg::R2 > 1) {
-            const float4 lo = stg4[2 * f], hi = stg4[2 * f + 1];
+            const float4 lo = stg4[f], hi = stg4[IOB4 + f];
             a = make_float4(lo.x * gs, lo.z * gs, hi.x * gs, hi.z * gs);
             b = make_float4(lo.y * gs, lo.w * gs, hi.y * gs, hi.w * gs);
           } else {
@@ -426,7 +432,6 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
     });
     env.sync_warp();
   }
-  env.sync_cluster();
 }
 
 }  // namespace favae

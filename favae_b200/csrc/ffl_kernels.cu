@@ -28,6 +28,14 @@ template <class Cfg> struct DevEnv {
     if constexpr (Cfg::C == 1) __syncthreads();
     else cg::this_cluster().sync();
   }
+  // split barrier: arrive = "my reads of S are done", wait = "everybody's are" (C == 1: a CTA barrier)
+  __device__ __forceinline__ void cluster_arrive() {
+    if constexpr (Cfg::C > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  }
+  __device__ __forceinline__ void cluster_wait() {
+    if constexpr (Cfg::C == 1) __syncthreads();
+    else asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   __device__ __forceinline__ ThreadRegs<Cfg>& regs(int, int) { return r; }
   __device__ __forceinline__ float2* S(int, int owner) {
     if constexpr (Cfg::C == 1) return s_;
@@ -60,9 +68,11 @@ ffl_kernel(const FflParams p) {
   if constexpr (Cfg::C == 1) env.rank_ = 0;
   else env.rank_ = (int)cg::this_cluster().block_rank();
   ffl_init_thread<Cfg>(env);
+  env.cluster_arrive();                          // opens the split barrier the first batch waits on
   const long long batches = (p.maps + Cfg::MPC - 1) / Cfg::MPC;
   const long long stride = gridDim.x / Cfg::C;
   for (long long b = blockIdx.x / Cfg::C; b < batches; b += stride) ffl_map_batch<Cfg>(env, p, b);
+  env.cluster_wait();                            // nobody leaves while a peer may still read its S
 }
 
 template <class Cfg> static int launch_ffl(const FflParams& p, cudaStream_t stream) {

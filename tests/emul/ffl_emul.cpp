@@ -30,6 +30,8 @@ template <class Cfg> struct HostEnv {
   void sync_warp() {}
   void sync_cta() {}
   void sync_cluster() {}
+  void cluster_arrive() {}
+  void cluster_wait() {}
   ThreadRegs<Cfg>& regs(int cta, int tid) { return regs_[cta * Cfg::THREADS + tid]; }
   float2* S(int, int owner) { return S_.data() + (size_t)owner * Cfg::S_FLOAT2; }
   float2* stg(int cta) { return stg_.data() + (size_t)cta * (Cfg::STG_FLOAT2 + 2); }
