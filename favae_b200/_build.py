@@ -29,16 +29,31 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cu'))
 
 
-def _deps_mtime():
-    m = 0.0
+def _source_digest():
+    """sha256 over every source the library is built from (paths + contents)."""
+    import hashlib
+    h = hashlib.sha256()
     for root in (CSRC, os.path.join(HERE, '..', 'include')):
-        for f in os.listdir(root):
-            m = max(m, os.path.getmtime(os.path.join(root, f)))
-    return m
+        for f in sorted(os.listdir(root)):
+            h.update(f.encode())
+            with open(os.path.join(root, f), 'rb') as fh:
+                h.update(fh.read())
+    h.update(' '.join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+STAMP = os.path.join(HERE, 'libfavae_b200.stamp')
 
 
 def needs_build():
-    return not os.path.exists(LIB) or os.path.getmtime(LIB) < _deps_mtime()
+    """True unless the library exists and was built from exactly the current sources.  A content
+    digest (not mtimes) decides, so a copied tree (gpurun snapshot) never triggers a rebuild."""
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
+        return True
+    try:
+        return open(STAMP).read().strip() != _source_digest()
+    except OSError:
+        return True
 
 
 def _compile(src):
@@ -61,6 +76,8 @@ def build(force=False, verbose=True):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
+    with open(STAMP, 'w') as fh:
+        fh.write(_source_digest())
     if verbose:
         print(f'[favae_b200] built {LIB}', file=sys.stderr)
     return LIB
