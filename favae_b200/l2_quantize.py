@@ -94,14 +94,15 @@ class _CodebookBase(nn.Module):
                  learnable_codebook=False, sample_codebook_temp=0.):
         super().__init__()
         if num_codebooks != 1:
-            raise NotImplementedError('favae_b200: multi-head / multiple codebooks are not built '
+            raise NotImplementedError('favae_b200: separate codebooks per head are not built '
                                       '(never used by FA-VAE, models/vqgan_fcm.py:103-105)')
-        if kmeans_init:
-            raise NotImplementedError('favae_b200: kmeans_init is not built (always False in FA-VAE)')
         if sample_codebook_temp != 0:
             raise NotImplementedError('favae_b200: gumbel sampling (sample_codebook_temp > 0) is not built')
-        if threshold_ema_dead_code != 0:
-            raise NotImplementedError('favae_b200: dead-code expiry (threshold_ema_dead_code > 0) is not built')
+        if use_ddp and (kmeans_init or threshold_ema_dead_code != 0):
+            raise NotImplementedError('favae_b200: distributed k-means init / dead-code expiry '
+                                      '(sample_vectors_distributed, :101-115) are not built')
+        self.kmeans_init = kmeans_init
+        self._init_done = not kmeans_init
         self.dim = dim
         self.decay = decay
         self.codebook_size = codebook_size
@@ -113,10 +114,13 @@ class _CodebookBase(nn.Module):
         self.use_ddp = use_ddp
         self.learnable_codebook = learnable_codebook
 
-        embed = uniform_init(num_codebooks, codebook_size, dim)
-        if self.cosine:
-            embed = l2norm(embed)
-        self.register_buffer('initted', torch.Tensor([True]))
+        if kmeans_init:
+            embed = torch.zeros(num_codebooks, codebook_size, dim)           # :200-201, :326-329
+        else:
+            embed = uniform_init(num_codebooks, codebook_size, dim)
+            if self.cosine:
+                embed = l2norm(embed)
+        self.register_buffer('initted', torch.Tensor([not kmeans_init]))
         self.register_buffer('cluster_size', torch.zeros(num_codebooks, codebook_size))
         if not self.cosine:
             self.register_buffer('embed_avg', embed.clone())
@@ -134,22 +138,14 @@ class _CodebookBase(nn.Module):
                   _lib.ptr(xh), None, _lib.stream())
         return xn, xh
 
-    def _search_and_gather(self, x, n, hw, straight_through, want_loss):
-        k, d, dev = self.codebook_size, self.dim, x.device
-        embed = self.embed.detach()[0]
-        if not embed.is_contiguous():
-            raise RuntimeError('favae_b200: codebook buffer must be contiguous')
-        mode = _search_mode()
-        use_tc = (self.cosine and mode != 'exact' and n > 0
-                  and _lib.load().favae_vq_search_tc_workspace_bytes(n, k, d) > 0)
-        if mode == 'tc' and not use_tc:
-            raise RuntimeError('favae_b200: FAVAE_VQ_SEARCH=tc but the tensor-core search does not '
-                               f'support dim={d}, codebook_size={k}')
+    def _search_rows(self, xn, xh, codes, n):
+        """Nearest code of every prepared latent row against ``codes`` (K, D).  Returns (idx, en)."""
+        k, d, dev = codes.shape[0], self.dim, xn.device
         idx = torch.empty((n,), device=dev, dtype=torch.int64)
         keys = torch.empty((n,), device=dev, dtype=torch.int64)
         if self.cosine:
-            xn, xh = self._prepare(x, n, hw, True, use_tc)
-            en, eh = self._prepare(embed, k, 1, True, use_tc)
+            use_tc = xh is not None
+            en, eh = self._prepare(codes, k, 1, True, use_tc)
             if use_tc:
                 ws_bytes = _lib.load().favae_vq_search_tc_workspace_bytes(n, k, d)
                 ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
@@ -159,13 +155,87 @@ class _CodebookBase(nn.Module):
                 _lib.call('favae_vq_search_exact', _lib.ptr(xn), _lib.ptr(en), None, n, k, d, 0,
                           _lib.ptr(keys), _lib.ptr(idx), _lib.stream())
         else:
-            xn, _ = self._prepare(x, n, hw, False, False)          # rearranged copy of x
             esq = torch.empty((k,), device=dev, dtype=torch.float32)
             en = torch.empty((k, d), device=dev, dtype=torch.float32)
-            _lib.call('favae_vq_prepare_rows', _lib.ptr(embed), k, d, 1, 0, _lib.ptr(en), None,
+            _lib.call('favae_vq_prepare_rows', _lib.ptr(codes), k, d, 1, 0, _lib.ptr(en), None,
                       _lib.ptr(esq), _lib.stream())
             _lib.call('favae_vq_search_exact', _lib.ptr(xn), _lib.ptr(en), _lib.ptr(esq), n, k, d, 1,
                       _lib.ptr(keys), _lib.ptr(idx), _lib.stream())
+        return idx, en
+
+    def _code_stats(self, rows, idx, n):
+        k, d = self.codebook_size, self.dim
+        stats = torch.empty((k * (d + 1),), device=rows.device, dtype=torch.float32)
+        _lib.call('favae_vq_code_stats', _lib.ptr(rows), _lib.ptr(idx), n, k, d, _lib.ptr(stats),
+                  _lib.stream())
+        return stats
+
+    @torch.no_grad()
+    def _kmeans_init(self, rows, xh, n):
+        """init_embed_ + kmeans (l2_quantize.py:124-164, :224-240, :351-367) on the prepared rows
+        (normalised for the cosine codebook, raw for the Euclidean one), built from the search and
+        statistics kernels.  Sampling uses the same torch RNG calls as the reference."""
+        if self._init_done:
+            return
+        if bool(self.initted):                   # e.g. a checkpoint was loaded
+            self._init_done = True
+            return
+        k, d = self.codebook_size, self.dim
+        if n >= k:
+            pick = torch.randperm(n, device=rows.device)[:k]
+        else:
+            pick = torch.randint(0, n, (k,), device=rows.device)
+        means = rows[pick].contiguous()
+        bins = torch.zeros(k, device=rows.device)
+        for _ in range(self.kmeans_iters):
+            idx, _ = self._search_rows(rows, xh, means, n)
+            stats = self._code_stats(rows, idx, n)
+            bins, esum = _dist.unpack_stats(stats, k, d)
+            zero = bins == 0
+            new_means = esum / bins.masked_fill(zero, 1.0)[:, None]
+            if self.cosine:
+                new_means = l2norm(new_means)
+            means = torch.where(zero[:, None], means, new_means).contiguous()
+        self.embed.data.copy_(means[None])
+        if not self.cosine:
+            self.embed_avg.data.copy_(means[None])
+        self.cluster_size.data.copy_(bins[None])
+        self.initted.data.fill_(1.0)
+        self._init_done = True
+
+    @torch.no_grad()
+    def _expire_codes(self, rows):
+        """expire_codes_ + replace (l2_quantize.py:242-262, :369-389): codes whose EMA cluster size
+        fell under the threshold are replaced by l2-normalised latents sampled from the batch."""
+        if self.threshold_ema_dead_code == 0:
+            return
+        expired = self.cluster_size[0] < self.threshold_ema_dead_code
+        num = int(expired.sum())                 # host sync, as in the reference (:376 .item())
+        if num == 0:
+            return
+        samples = rows if self.cosine else l2norm(rows)     # the reference normalises in both classes
+        n = samples.shape[0]
+        if n >= num:
+            pick = torch.randperm(n, device=rows.device)[:num]
+        else:
+            pick = torch.randint(0, n, (num,), device=rows.device)
+        self.embed.data[0][expired] = samples[pick]
+
+    def _search_and_gather(self, x, n, hw, straight_through, want_loss):
+        k, d, dev = self.codebook_size, self.dim, x.device
+        mode = _search_mode()
+        use_tc = (self.cosine and mode != 'exact' and n > 0
+                  and _lib.load().favae_vq_search_tc_workspace_bytes(n, k, d) > 0)
+        if mode == 'tc' and not use_tc:
+            raise RuntimeError('favae_b200: FAVAE_VQ_SEARCH=tc but the tensor-core search does not '
+                               f'support dim={d}, codebook_size={k}')
+        # rows: l2-normalised latents (cosine) or the rearranged raw latents (Euclidean)
+        xn, xh = self._prepare(x, n, hw, self.cosine, use_tc)
+        self._kmeans_init(xn, xh, n)
+        embed = self.embed.detach()[0]
+        if not embed.is_contiguous():
+            raise RuntimeError('favae_b200: codebook buffer must be contiguous')
+        idx, en = self._search_rows(xn, xh, embed, n)
 
         out = torch.empty_like(x)
         loss_sum = torch.zeros((1,), device=dev, dtype=torch.float32)
@@ -176,13 +246,12 @@ class _CodebookBase(nn.Module):
                   _lib.ptr(loss_sum) if want_loss else None, _lib.stream())
 
         if self.training:
-            stats = torch.empty((k * (d + 1),), device=dev, dtype=torch.float32)
-            _lib.call('favae_vq_code_stats', _lib.ptr(xn), _lib.ptr(idx), n, k, d, _lib.ptr(stats),
-                      _lib.stream())
+            stats = self._code_stats(xn, idx, n)
             if self.use_ddp:
                 # one all-reduce of [bins | embed_sum] (reference: two, :419/:427 and :291/:295)
                 _dist.all_reduce_stats(stats)
             self._ema_update(en, stats)
+            self._expire_codes(xn)
         return out, idx, loss_sum
 
     def _ema_update(self, en, stats):
@@ -229,8 +298,9 @@ class VectorQuantize(nn.Module):
                  commitment_weight=1., orthogonal_reg_weight=0., orthogonal_reg_active_codes_only=False,
                  orthogonal_reg_max_codes=None, sample_codebook_temp=0., sync_codebook=False):
         super().__init__()
-        if heads != 1 or separate_codebook_per_head:
-            raise NotImplementedError('favae_b200: heads > 1 is not built (FA-VAE uses heads=1)')
+        if separate_codebook_per_head and heads > 1:
+            raise NotImplementedError('favae_b200: separate codebooks per head are not built '
+                                      '(FA-VAE uses heads=1)')
         self.heads = heads
         self.separate_codebook_per_head = separate_codebook_per_head
 
@@ -287,12 +357,13 @@ class VectorQuantize(nn.Module):
         device = x.device
         need_transpose = not self.channel_last and not self.accept_image_fmap
         projected = not isinstance(self.project_in, nn.Identity)
+        heads = self.heads
         cb = self._codebook
         training = self.training
 
         if self.accept_image_fmap:
             b, _, height, width = x.shape
-            if projected:
+            if projected or heads > 1:
                 x = x.permute(0, 2, 3, 1).reshape(b, height * width, -1)      # :540
                 hw = 1
             else:
@@ -302,6 +373,9 @@ class VectorQuantize(nn.Module):
             if need_transpose:
                 x = x.transpose(1, 2)        # 'b d n -> b n d'
         x = self.project_in(x)
+        if heads > 1:                        # shared codebook: 'b n (h d) -> 1 (b h) n d'  (:547-549)
+            bb, nn_ = x.shape[0], x.shape[1]
+            x = x.reshape(bb, nn_, heads, -1).permute(0, 2, 1, 3)
         x = x.float().contiguous()
         if x.shape[1 if hw > 1 else -1] != cb.dim:
             raise RuntimeError(f'expected {cb.dim} channels, got {tuple(x.shape)}')
@@ -327,13 +401,16 @@ class VectorQuantize(nn.Module):
                     codebook = codebook[:, rand_ids]
                 loss = loss + orthogonal_loss_fn(codebook) * self.orthogonal_reg_weight
 
+        if heads > 1:                        # '1 (b h) n d -> b n (h d)', '1 (b h) n -> b n h'  (:579-585)
+            quantize = quantize.permute(0, 2, 1, 3).reshape(bb, nn_, -1)
+            idx = idx.view(bb, heads, nn_).permute(0, 2, 1)
         quantize = self.project_out(quantize)
         if self.accept_image_fmap:
-            if projected:
+            if projected or heads > 1:
                 quantize = quantize.reshape(b, height, width, -1).permute(0, 3, 1, 2)
-            embed_ind = idx.view(b, height, width)
+            embed_ind = idx.reshape(b, height, width, heads) if heads > 1 else idx.view(b, height, width)
         else:
             if need_transpose:
                 quantize = quantize.transpose(1, 2)
-            embed_ind = idx.view(x.shape[:-1])
+            embed_ind = idx if heads > 1 else idx.view(x.shape[:-1])
         return quantize, embed_ind, loss

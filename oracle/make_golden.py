@@ -39,15 +39,15 @@ def _np(t):
     return t.detach().cpu().numpy().copy()      # copy: buffers are updated in place later
 
 
-def vq_case(l2q, name, *, K, D, B, h, w, cosine, steps, commit=1.0, dim=None, seed=0):
+def vq_case(l2q, name, *, K, D, B, h, w, cosine, steps, commit=1.0, dim=None, seed=0, heads=1):
     torch.manual_seed(seed)
-    dim = D if dim is None else dim
+    dim = D * heads if dim is None else dim
     vq = l2q.VectorQuantize(dim=dim, codebook_size=K, codebook_dim=D, accept_image_fmap=True,
-                            use_cosine_sim=cosine, commitment_weight=commit)
+                            use_cosine_sim=cosine, commitment_weight=commit, heads=heads)
     vq.train()
-    rec = {'K': K, 'D': D, 'dim': dim, 'cosine': int(cosine), 'commit': commit, 'steps': steps,
+    rec = {'K': K, 'D': D, 'dim': dim, 'cosine': int(cosine), 'commit': commit, 'steps': steps, 'heads': heads,
            'embed0': _np(vq._codebook.embed[0]), 'cluster0': _np(vq._codebook.cluster_size[0])}
-    if dim != D:
+    if dim != D * heads:
         rec.update(pin_w=_np(vq.project_in.weight), pin_b=_np(vq.project_in.bias),
                    pout_w=_np(vq.project_out.weight), pout_b=_np(vq.project_out.bias))
     if not cosine:
@@ -55,7 +55,7 @@ def vq_case(l2q, name, *, K, D, B, h, w, cosine, steps, commit=1.0, dim=None, se
     g = torch.Generator().manual_seed(1234 + seed)
     for s in range(steps):
         x = torch.randn(B, dim, h, w, generator=g)
-        if s == 0 and cosine and dim == D:
+        if s == 0 and cosine and dim == D and heads == 1:
             # plant exact ties: two latents sit exactly on duplicated codes
             vq._codebook.embed[0, 5] = vq._codebook.embed[0, 3]
             rec['embed0'] = _np(vq._codebook.embed[0])
@@ -73,7 +73,7 @@ def vq_case(l2q, name, *, K, D, B, h, w, cosine, steps, commit=1.0, dim=None, se
     x = torch.randn(B, dim, h, w, generator=g)
     q, ind, loss = vq(x)
     rec.update(x_eval=_np(x), q_eval=_np(q), ind_eval=_np(ind), loss_eval=_np(loss))
-    if dim == D:
+    if dim == D and heads == 1:
         ids = torch.randint(0, K, (B, h * w), generator=g)
         rec.update(entry_ids=_np(ids), entry=_np(vq.get_codebook_entry(ids, (B, h, w, D))))
     np.savez_compressed(os.path.join(OUT, f'vq_{name}.npz'), **rec)
@@ -180,6 +180,7 @@ def main():
     vq_case(l2q, 'cos_mid', K=512, D=64, B=2, h=8, w=8, cosine=True, steps=3, commit=1.0, seed=1)
     vq_case(l2q, 'cos_proj', K=128, D=32, B=2, h=8, w=8, cosine=True, steps=2, dim=3, seed=2)
     vq_case(l2q, 'euclid_small', K=64, D=32, B=2, h=4, w=4, cosine=False, steps=2, seed=3)
+    vq_case(l2q, 'cos_heads2', K=64, D=32, B=2, h=4, w=4, cosine=True, steps=2, seed=4, heads=2)
     vq_ddp_case('cos_ddp2')
     blur_cases(VQGANFCM)
     wrapper_cases(vl)

@@ -55,8 +55,8 @@ def test_no_cpu_fallback_and_unsupported_options():
         FocalFrequencyLoss()(torch.zeros(1, 1, 8, 8), torch.zeros(1, 1, 8, 8))
     with pytest.raises(RuntimeError, match='CUDA'):
         gaussian_blur_reflect(torch.zeros(1, 1, 8, 8), 1.0, 3)
-    for kw in (dict(heads=2), dict(kmeans_init=True), dict(sample_codebook_temp=1.0),
-               dict(threshold_ema_dead_code=2)):
+    for kw in (dict(heads=2, separate_codebook_per_head=True), dict(sample_codebook_temp=1.0),
+               dict(kmeans_init=True, sync_codebook=True), dict(threshold_ema_dead_code=2, sync_codebook=True)):
         with pytest.raises(NotImplementedError):
             VectorQuantize(dim=8, codebook_size=16, **kw)
 

@@ -38,12 +38,13 @@ def _module(g, sync=False):
     from favae_b200 import VectorQuantize
     vq = VectorQuantize(dim=int(g['dim']), codebook_size=int(g['K']), codebook_dim=int(g['D']),
                         accept_image_fmap=True, use_cosine_sim=bool(g['cosine']),
-                        commitment_weight=float(g['commit']), sync_codebook=sync).cuda()
+                        commitment_weight=float(g['commit']), sync_codebook=sync,
+                        heads=int(g['heads']) if 'heads' in g else 1).cuda()
     sd = {'_codebook.initted': torch.ones(1), '_codebook.cluster_size': _t(g['cluster0'], 'cpu')[None],
           '_codebook.embed': _t(g['embed0'], 'cpu')[None]}
     if not bool(g['cosine']):
         sd['_codebook.embed_avg'] = _t(g['embed_avg0'], 'cpu')[None]
-    if int(g['dim']) != int(g['D']):
+    if int(g['dim']) != int(g['D']) * (int(g['heads']) if 'heads' in g else 1):
         sd.update({'project_in.weight': _t(g['pin_w'], 'cpu'), 'project_in.bias': _t(g['pin_b'], 'cpu'),
                    'project_out.weight': _t(g['pout_w'], 'cpu'), 'project_out.bias': _t(g['pout_b'], 'cpu')})
     missing = vq.load_state_dict(sd, strict=True)      # same keys as the reference module
@@ -51,14 +52,15 @@ def _module(g, sync=False):
     return vq
 
 
-@pytest.mark.parametrize('name', ['cos_small', 'cos_mid', 'cos_proj', 'euclid_small'])
+@pytest.mark.parametrize('name', ['cos_small', 'cos_mid', 'cos_proj', 'euclid_small', 'cos_heads2'])
 @pytest.mark.parametrize('mode', ['exact', 'auto'])
 def test_golden_replay(golden_dir, name, mode, monkeypatch):
     monkeypatch.setenv('FAVAE_VQ_SEARCH', mode)
     g = np.load(os.path.join(golden_dir, f'vq_{name}.npz'))
     vq = _module(g).train()
     cosine, D = bool(g['cosine']), int(g['D'])
-    proj = int(g['dim']) != D
+    heads = int(g['heads']) if 'heads' in g else 1
+    proj = int(g['dim']) != D or heads > 1          # no flat (N, D) view of x to re-score near-ties with
     for s in range(int(g['steps'])):
         x = _t(g[f'x{s}']).requires_grad_(True)
         embed_before = vq._codebook.embed[0].clone()
@@ -158,9 +160,45 @@ def test_edge_cases():
     with pytest.raises(RuntimeError):
         vq(torch.zeros(1, 64, 2, 2))                       # CPU tensor: no fallback
     with pytest.raises(NotImplementedError):
-        VectorQuantize(dim=64, codebook_size=128, heads=2)
+        VectorQuantize(dim=64, codebook_size=128, heads=2, separate_codebook_per_head=True)
     with pytest.raises(NotImplementedError):
-        VectorQuantize(dim=64, codebook_size=128, kmeans_init=True)
+        VectorQuantize(dim=64, codebook_size=128, sample_codebook_temp=0.5)
+
+
+def test_kmeans_init_and_dead_code_expiry():
+    """Cold options of the reference (kmeans :124-164, expire_codes_ :369-389) built on the search and
+    statistics kernels.  Sampling is RNG dependent, so properties are checked instead of fixtures."""
+    from favae_b200 import VectorQuantize
+    torch.manual_seed(0)
+    K, D = 32, 64
+    centers = torch.nn.functional.normalize(torch.randn(K, D, device='cuda'), dim=-1)
+    x = (centers[torch.randint(0, K, (4 * 16 * 16,), device='cuda')] + 0.01 * torch.randn(1024, D, device='cuda'))
+    x = x.view(4, 16, 16, D).permute(0, 3, 1, 2).contiguous()
+    vq = VectorQuantize(dim=D, codebook_size=K, accept_image_fmap=True, use_cosine_sim=True, kmeans_init=True,
+                        kmeans_iters=10).cuda().train()
+    assert float(vq._codebook.initted) == 0.0 and float(vq._codebook.embed.abs().sum()) == 0.0
+    q, ind, loss = vq(x)
+    assert float(vq._codebook.initted) == 1.0
+    torch.testing.assert_close(vq._codebook.embed[0].norm(dim=-1).clamp(max=1.0001),
+                               vq._codebook.embed[0].norm(dim=-1))          # EMA of unit vectors: norms <= 1
+    # k-means on well separated clusters: most latents end within a small angle of their code
+    # (random seeding can merge two clusters, as in the reference)
+    qn = torch.nn.functional.normalize(q.permute(0, 2, 3, 1).reshape(-1, D), dim=-1)
+    xn = torch.nn.functional.normalize(x.permute(0, 2, 3, 1).reshape(-1, D), dim=-1)
+    cos = (qn * xn).sum(-1)
+    assert float(cos.median()) > 0.98 and float(cos.mean()) > 0.9
+    assert float(loss) < 0.5
+    # dead-code expiry: codes that never win are re-seeded with normalised latents of the batch
+    vq2 = VectorQuantize(dim=D, codebook_size=128, accept_image_fmap=True, use_cosine_sim=True,
+                         threshold_ema_dead_code=2).cuda().train()
+    before = vq2._codebook.embed[0].clone()
+    vq2(x)
+    dead = vq2._codebook.cluster_size[0] < 2
+    assert int(dead.sum()) > 0
+    after = vq2._codebook.embed[0]
+    sims = (after[dead] @ xn.t()).amax(dim=-1)
+    torch.testing.assert_close(sims, torch.ones_like(sims), rtol=0, atol=1e-5)   # each is a batch latent
+    assert not torch.equal(after[dead], before[dead])
 
 
 def _tc_search(x, embed):
