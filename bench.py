@@ -193,7 +193,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          '-lms', '50', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -219,11 +219,12 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     batch = 1
-    value, ms = time_cpu(batch, args.steps, min(args.warmup, 1))
+    steps = max(1, min(args.steps, 20))           # bounded sample: ~0.35 s of host work per step
+    value, ms = time_cpu(batch, steps, min(args.warmup, 1))
     line = base_line(args, world, value, ms, impl='reference')
     line.update({'impl': 'reference', 'dtype': 'f32', 'gpu_launches': 0,
                  'cpu_baseline': {'value': value, 'unit': 'img/s', 'cores': os.cpu_count(), 'kind': 'port',
-                                  'sample': f'{args.steps} steps of the full hot-path step at batch {batch} '
+                                  'sample': f'{steps} steps of the full hot-path step at batch {batch} '
                                             f'(oracle/ torch-CPU port of the reference, all host threads)'},
                  'e2e': {'value': value, 'unit': 'img/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}})
     print(json.dumps(line), flush=True)
@@ -245,8 +246,8 @@ def base_line(args, world, value, ms, impl='favae_b200'):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--batch', type=int, default=32, help='images per GPU')
     ap.add_argument('--impl', default='favae_b200', choices=['favae_b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -161,3 +161,59 @@ def test_dsl_gradients_reach_sigma_and_features():
     assert (dg.grad.cpu().double() - dd.grad).abs().max() <= RTOL * dd.grad.abs().max()
     assert float(s1.grad) == pytest.approx(float(t1.grad), rel=2e-3)
     assert float(s2.grad) == pytest.approx(float(t2.grad), rel=2e-3)
+
+
+def test_f4_config_end_to_end_vs_oracle():
+    """BASELINE configs[3] (ImageNet f=4): 64x64 latent grid, dim 3 -> codebook_dim 256 projection,
+    K = 8192, gaussian_kernel 3, feature levels (128,256,256) / (512,64,64) x2 / (3,64,64); batch 1.
+    Quantizer + DSL wrapper forward/backward against the oracle."""
+    from favae_b200 import FocalFrequencyLoss, VectorQuantize, gaussian_blur_reflect
+    from favae_b200 import vqgan_losses as vl
+    from oracle import vq_oracle as vo
+    from oracle import wrappers_oracle as wo
+    torch.manual_seed(0)
+    vq = VectorQuantize(dim=3, codebook_size=8192, codebook_dim=256, accept_image_fmap=True,
+                        use_cosine_sim=True, commitment_weight=1.0).cuda().train()
+    z = torch.randn(1, 3, 64, 64, generator=torch.Generator().manual_seed(1))
+    zg = z.cuda().requires_grad_(True)
+    embed0 = vq._codebook.embed[0].clone().cpu()          # the search uses the pre-update codebook
+    q, ind, loss_q = vq(zg)
+    assert q.shape == (1, 3, 64, 64) and ind.shape == (1, 64, 64) and loss_q.shape == (1,)
+    # oracle on the projected latents (same Linear weights)
+    w_in, b_in = vq.project_in.weight.detach().cpu(), vq.project_in.bias.detach().cpu()
+    flat = z.permute(0, 2, 3, 1).reshape(-1, 3) @ w_in.t() + b_in
+    shapes = [(1, 128, 256, 256), (1, 512, 64, 64), (1, 512, 64, 64), (1, 3, 64, 64)]
+    g = torch.Generator().manual_seed(2)
+    en = [torch.randn(*s, generator=g) for s in shapes]
+    de = [torch.randn(*s, generator=g) for s in reversed(shapes)]
+    dsl = FocalFrequencyLoss(loss_weight=0.01)
+    eg = [t.cuda().requires_grad_(True) for t in en]
+    dg = [t.cuda().requires_grad_(True) for t in de]
+    sig = torch.full((8,), 3.0, device='cuda', requires_grad=True)
+    eb = [gaussian_blur_reflect(eg[i], sig[i], 3) for i in range(4)]
+    db = [gaussian_blur_reflect(dg[i], sig[4 + i], 3) for i in range(4)]
+    loss, lst = vl.recon_ffl_features_loss(dsl, eb, db, 'cuda')
+    (loss.sum() + loss_q.sum()).backward()
+    # reference side (levels 1..3 on the CPU oracle in fp32; level 0 is covered by other tests)
+    from oracle import blur_oracle as bo
+    dslo = fo.FocalFrequencyLossOracle(loss_weight=0.01)
+    ed = [t.clone().requires_grad_(True) for t in en]
+    dd = [t.clone().requires_grad_(True) for t in de]
+    so = torch.full((8,), 3.0, requires_grad=True)
+    ebo = [bo.gaussian_blur_reflect(ed[i], so[i], 3) for i in range(4)]
+    dbo = [bo.gaussian_blur_reflect(dd[i], so[4 + i], 3) for i in range(4)]
+    lo, lsto = wo.recon_ffl_features_loss(dslo, ebo, dbo)
+    lo.sum().backward()
+    np.testing.assert_allclose(loss.item(), lo.item(), rtol=RTOL)
+    np.testing.assert_allclose([float(v) for v in lst], [float(v) for v in lsto], rtol=RTOL)
+    for a, b in zip(eg + dg, ed + dd):
+        assert (a.grad.cpu() - b.grad).abs().max() <= 2e-4 * b.grad.abs().max()
+    np.testing.assert_allclose(sig.grad.cpu().numpy(), so.grad.numpy(), rtol=5e-3, atol=1e-7)
+    # quantizer: indices vs oracle on the projected latents (near-ties allowed by score gap)
+    idx_o, xn_o, en_o = vo.cosine_search(flat, embed0)
+    bad = (ind.reshape(-1).cpu() != idx_o).nonzero().flatten()
+    if bad.numel():        # the projected latents span only 3 dimensions: near-ties are common
+        sg = (xn_o[bad].double() * en_o[ind.reshape(-1).cpu()[bad]].double()).sum(-1)
+        sr = (xn_o[bad].double() * en_o[idx_o[bad]].double()).sum(-1)
+        assert (sg - sr).abs().max() <= 1e-6 and bad.numel() <= 40
+    assert zg.grad is not None and torch.isfinite(zg.grad).all()
