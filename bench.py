@@ -222,7 +222,7 @@ def run_reference(args, rank, world):
     steps = max(1, min(args.steps, 20))           # bounded sample: ~0.35 s of host work per step
     value, ms = time_cpu(batch, steps, min(args.warmup, 1))
     line = base_line(args, world, value, ms, impl='reference')
-    line.update({'impl': 'reference', 'dtype': 'f32', 'gpu_launches': 0,
+    line.update({'impl': 'reference', 'dtype': 'f32', 'gpu_launches': 0, 'steps': steps, 'warmup': min(args.warmup, 1),
                  'cpu_baseline': {'value': value, 'unit': 'img/s', 'cores': os.cpu_count(), 'kind': 'port',
                                   'sample': f'{steps} steps of the full hot-path step at batch {batch} '
                                             f'(oracle/ torch-CPU port of the reference, all host threads)'},
