@@ -44,8 +44,15 @@ static inline float4 make_float4(float x, float y, float z, float w) { float4 r;
 
 #if defined(__CUDA_ARCH__)
 #define FAVAE_RSQRT(x) rsqrtf(x)
+// single-instruction square root (MUFU.SQRT, relative error <= 2^-23, sqrt(0) = 0)
+__device__ __forceinline__ float favae_fast_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 #else
 #define FAVAE_RSQRT(x) (1.0f / sqrtf(x))
+static inline float favae_fast_sqrt(float x) { return sqrtf(x); }
 #endif
 
 namespace favae {
@@ -53,8 +60,38 @@ namespace favae {
 // ----------------------------------------------------------------------------------
 // complex helpers
 // ----------------------------------------------------------------------------------
-FAVAE_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-FAVAE_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// Packed fp32x2 arithmetic: sm_100a executes add/mul/fma on a register pair in one issue slot
+// (FADD2 / FMUL2 / FFMA2, same lane throughput as the scalar forms - profiles/tools/ffma2_bench.cu),
+// which halves the instruction count of the complex butterflies.  The host build (emulation) uses
+// the scalar forms; results are bit-identical (each lane is an IEEE fp32 op either way).
+#if defined(__CUDA_ARCH__) && !defined(FAVAE_FFL_NO_PACKED)
+#define FAVAE_PK_ASM(op)                                                                              \
+  float2 c;                                                                                           \
+  asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; " op " rc, ra, rb; mov.b64 {%0,%1}, rc;}" \
+      : "=f"(c.x), "=f"(c.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                              \
+  return c;
+FAVAE_HD float2 pk_add(float2 a, float2 b) { FAVAE_PK_ASM("add.f32x2") }
+FAVAE_HD float2 pk_sub(float2 a, float2 b) { FAVAE_PK_ASM("sub.f32x2") }
+FAVAE_HD float2 pk_mul(float2 a, float2 b) { FAVAE_PK_ASM("mul.f32x2") }
+#undef FAVAE_PK_ASM
+FAVAE_HD float2 pk_fma(float2 a, float2 b, float2 d) {   // a * b + d, fused per lane
+  float2 c;
+  asm("{.reg .b64 ra, rb, rd, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rd, {%6,%7}; "
+      "fma.rn.f32x2 rc, ra, rb, rd; mov.b64 {%0,%1}, rc;}"
+      : "=f"(c.x), "=f"(c.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(d.x), "f"(d.y));
+  return c;
+}
+#else
+FAVAE_HD float2 pk_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+FAVAE_HD float2 pk_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+FAVAE_HD float2 pk_mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+FAVAE_HD float2 pk_fma(float2 a, float2 b, float2 d) { return make_float2(fmaf(a.x, b.x, d.x), fmaf(a.y, b.y, d.y)); }
+#endif
+FAVAE_HD float2 pk_swap(float2 a) { return make_float2(a.y, a.x); }
+FAVAE_HD float2 pk_dup(float v) { return make_float2(v, v); }
+
+FAVAE_HD float2 cadd(float2 a, float2 b) { return pk_add(a, b); }
+FAVAE_HD float2 csub(float2 a, float2 b) { return pk_sub(a, b); }
 FAVAE_HD float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -63,7 +100,8 @@ template <int DIR> FAVAE_HD float2 crot(float2 a) {
   return DIR < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
 }
 
-// twiddle e^{DIR * 2*pi*i * j/16}, j = 0..7, as compile-time constants
+// twiddle e^{DIR * 2*pi*i * j/16}, j = 0..7, as compile-time constants:
+// a * (c + i s) = a (.) (c, c) + swap(a) (.) (-s, s), two packed operations
 template <int J, int DIR> FAVAE_HD float2 ctw16(float2 a) {
   constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
   if constexpr (J == 0) return a;
@@ -72,7 +110,7 @@ template <int J, int DIR> FAVAE_HD float2 ctw16(float2 a) {
     constexpr float c = (J == 1) ? C1 : (J == 2) ? R2 : (J == 3) ? S1 : (J == 5) ? -S1 : (J == 6) ? -R2 : -C1;
     constexpr float s0 = (J == 1) ? S1 : (J == 2) ? R2 : (J == 3) ? C1 : (J == 5) ? C1 : (J == 6) ? R2 : S1;
     constexpr float s = DIR < 0 ? -s0 : s0;
-    return make_float2(a.x * c - a.y * s, a.x * s + a.y * c);
+    return pk_fma(pk_swap(a), make_float2(-s, s), pk_mul(a, make_float2(c, c)));
   }
 }
 
@@ -132,7 +170,14 @@ template <int N_, int C_, int MPC_, int THREADS_> struct FflCfg {
   static constexpr int ITEMS = MPC * HALF / C;     // row pairs (= column groups) per CTA
   static constexpr int PASSES = ITEMS / NG;
   static constexpr int COLSTRIDE = HALF + 1;       // float2 per S column (padded)
-  static constexpr int S_FLOAT2 = MPC * (N / C) * COLSTRIDE;
+  // S holds, per CTA, N/C map columns x HALF entries (row pair r' in P1/P6, frequency u in P2..P5).
+  // One CTA per map: column-major (entry index contiguous).  Clusters: entry-major, S[entry][column]
+  // with an odd row stride, so that the 16 lanes of a row FFT write / read 16 adjacent columns of
+  // the peer CTA as one 128-byte distributed-shared-memory segment instead of 16 scattered 8-byte
+  // words, while the column FFTs (stride COLSTRIDE) stay bank-conflict free.
+  static constexpr bool S_ENTRY_MAJOR = C > 1;
+  static constexpr int S_IDX = S_ENTRY_MAJOR ? (N / C + 1) : 1;
+  static constexpr int S_FLOAT2 = S_ENTRY_MAJOR ? HALF * (N / C + 1) : MPC * (N / C) * COLSTRIDE;
   static constexpr int STG_STRIDE = R2 + 1;
   static constexpr int STG_FLOAT2 = (R2 > 1) ? NG * R1 * STG_STRIDE : 1;
   static constexpr int PO_IN = R1 / 2;                         // register offset of n + N/2
@@ -192,7 +237,8 @@ template <class Cfg> FAVAE_HD void s_locate(int w, int slot_map, int& owner, int
   else if (w < HALF) { group = w; sub = 0; }
   else { group = N - w; sub = 1; }
   owner = group / GPC;
-  off = ((slot_map * GPC + (group % GPC)) * 2 + sub) * Cfg::COLSTRIDE;
+  if constexpr (Cfg::S_ENTRY_MAJOR) off = sub * GPC + (group % GPC);   // adjacent map columns stay adjacent
+  else off = ((slot_map * GPC + (group % GPC)) * 2 + sub) * Cfg::COLSTRIDE;
 }
 
 // f(A) from A^2 (already ortho-normalised)
@@ -219,7 +265,7 @@ template <class Cfg> FAVAE_HD void s_lookup(const unsigned int* tab, int w, int 
   constexpr int GPC = Cfg::HALF / Cfg::C;
   const unsigned int e = tab[w];
   owner = (int)(e >> 24);
-  off = (int)(e & 0xFFFFFFu) + slot_map * (GPC * 2 * Cfg::COLSTRIDE);
+  off = (int)(e & 0xFFFFFFu) + (Cfg::S_ENTRY_MAJOR ? 0 : slot_map * (GPC * 2 * Cfg::COLSTRIDE));
 }
 
 // ----------------------------------------------------------------------------------

@@ -3,7 +3,7 @@
 // `Env` abstracts the execution model so that the same phases run as a CUDA thread
 // block / cluster (ffl_kernels.cu) and as plain loops on the host (tests/emul):
 //   env.for_threads(f)   f(cta, tid) for every thread of every CTA of the cluster
-//   env.sync_warp/cta/cluster()   env.cluster_arrive() / env.cluster_wait(): split cluster barrier
+//   env.sync_warp/cta/cluster()   env.cluster_arrive[_relaxed]() / env.cluster_wait(): split cluster barrier
 //   env.regs(cta, tid)   ThreadRegs that persist across sync points
 //   env.S(cta, owner)    float2* to the spectrum buffer of CTA `owner` as seen from `cta`
 //   env.stg(cta)         staging for the two-stage 1-D FFT exchange
@@ -12,6 +12,7 @@
 //   env.cl(cta, owner)   float* to the cluster slots of CTA `owner`
 //   env.tab(cta)         N packed S addresses (s_pack), built by ffl_init_thread
 //   env.twiddle(j, n)    e^{-2 pi i j / n}
+//   env.prefetch_l2(ptr, bytes)   hint: bring a 16-byte-aligned global range into L2
 #pragma once
 
 #include "ffl_core.cuh"
@@ -32,15 +33,21 @@ FAVAE_HD void ffl_init_thread(Env& env) {
 }
 
 // One batch = MPC maps (C == 1) or one map shared by the C CTAs of a cluster.
-template <class Cfg, class Env>
-FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
+// FAST: the reference's configuration (alpha == 1, no log weighting), where f(A) = A = sqrt(m)/N with
+// m = |D|^2 unnormalised.  The spectrum statistics then run on m (sum m*sqrt(m), max m: the maximum
+// commutes with the monotone f) and are converted once per thread, and the weight is
+// min(sqrt(m) / sqrt(m_max), 1): 5-6 instructions per bin instead of ~12.
+template <class Cfg, bool FAST = false, class Env>
+FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long long next_batch = -1) {
   constexpr int N = Cfg::N, R1 = Cfg::R1, TG = Cfg::TG, NG = Cfg::NG, HALF = Cfg::HALF;
   constexpr int C = Cfg::C, MPC = Cfg::MPC, T = Cfg::THREADS, PASSES = Cfg::PASSES;
   constexpr int GPC = HALF / C;                 // row pairs / column groups per CTA and map
   constexpr int TMAP = T / MPC;                 // threads per map slot
   constexpr int STG = R1 * Cfg::STG_STRIDE;
+  constexpr int IS = Cfg::S_IDX;                // S stride of the row / frequency index
   static_assert(MPC == 1 || PASSES == 1, "several maps per CTA need a single pass");
   const float inv_nn = 1.0f / (float)(N * N);
+  const float inv_n = 1.0f / (float)N;
   const long long map0 = batch * MPC;
 
   env.for_threads([&](int cta, int tid) {
@@ -48,6 +55,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
     r.sum = 0.0f; r.mx = 0.0f;
   });
 
+  env.mark(-1);
   // ---------------- P1: packed row FFTs, global -> S ----------------
   // Inputs are read as float4 (each thread IO_V4 vectors per row and tensor) and redistributed to
   // the FFT's strided layout through the group's staging area.
@@ -62,18 +70,24 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       const bool live = map < p.maps;
       const long long base = map * (long long)(N * N) + rp * N;
       float4* stg4 = reinterpret_cast<float4*>(env.stg(cta) + g * STG);
+      // all 4*V4 loads are issued before the first use: one HBM round trip per pass
+      float4 pa[V4], ta[V4], pb[V4], tb[V4];
 #pragma unroll
       for (int j = 0; j < V4; ++j) {
         const int f = t + TG * j;                        // float4 index inside the row
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        pa[j] = ta[j] = pb[j] = tb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (live) {
-          const float4 pa = *reinterpret_cast<const float4*>(p.pred + base + 4 * f);
-          const float4 ta = *reinterpret_cast<const float4*>(p.target + base + 4 * f);
-          const float4 pb = *reinterpret_cast<const float4*>(p.pred + base + HALF * N + 4 * f);
-          const float4 tb = *reinterpret_cast<const float4*>(p.target + base + HALF * N + 4 * f);
-          a = make_float4(pa.x - ta.x, pa.y - ta.y, pa.z - ta.z, pa.w - ta.w);
-          b = make_float4(pb.x - tb.x, pb.y - tb.y, pb.z - tb.z, pb.w - tb.w);
+          pa[j] = *reinterpret_cast<const float4*>(p.pred + base + 4 * f);
+          ta[j] = *reinterpret_cast<const float4*>(p.target + base + 4 * f);
+          pb[j] = *reinterpret_cast<const float4*>(p.pred + base + HALF * N + 4 * f);
+          tb[j] = *reinterpret_cast<const float4*>(p.target + base + HALF * N + 4 * f);
         }
+      }
+#pragma unroll
+      for (int j = 0; j < V4; ++j) {
+        const int f = t + TG * j;
+        const float4 a = make_float4(pa[j].x - ta[j].x, pa[j].y - ta[j].y, pa[j].z - ta[j].z, pa[j].w - ta[j].w);
+        const float4 b = make_float4(pb[j].x - tb[j].x, pb[j].y - tb[j].y, pb[j].z - tb[j].z, pb[j].w - tb[j].w);
         if constexpr (Cfg::R2 > 1) {                     // interleave (row r', row r'+N/2) pairs
           stg4[f] = make_float4(a.x, b.x, a.y, b.y);          // elements 4f, 4f+1
           stg4[IOB4 + f] = make_float4(a.z, b.z, a.w, b.w);   // elements 4f+2, 4f+3 (bank-shifted half)
@@ -94,6 +108,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       }
     });
     env.sync_warp();
+    env.mark(0);
     env.for_threads([&](int cta, int tid) {
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
       const int g = tid / TG, t = tid % TG;
@@ -114,12 +129,33 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       for (int e = 0; e < R1; ++e) {
         int owner, off;
         s_lookup<Cfg>(tab, idx_out<Cfg>(t, e), m, owner, off);
-        env.S(cta, owner)[off + rp] = r.v[e];
+        env.S(cta, owner)[off + IS * rp] = r.v[e];
       }
     });
     env.sync_warp();
+    env.mark(1);
   }
   env.sync_cluster();
+  env.mark(2);
+  // pull the next batch's rows of this CTA into L2 while this one is transformed (one bulk
+  // prefetch per contiguous run of rows; a hint only)
+  if (next_batch >= 0 && next_batch * MPC < p.maps) {
+    env.for_threads([&](int cta, int tid) {
+      if (tid == 0) {
+        const long long nmaps = (p.maps - next_batch * MPC < MPC) ? p.maps - next_batch * MPC : MPC;
+        if constexpr (C == 1) {
+          env.prefetch_l2(p.pred + next_batch * MPC * (long long)(N * N), nmaps * N * N * sizeof(float));
+          env.prefetch_l2(p.target + next_batch * MPC * (long long)(N * N), nmaps * N * N * sizeof(float));
+        } else {
+          const long long base = next_batch * (long long)(N * N) + (long long)cta * GPC * N;
+          env.prefetch_l2(p.pred + base, GPC * N * sizeof(float));
+          env.prefetch_l2(p.pred + base + HALF * N, GPC * N * sizeof(float));
+          env.prefetch_l2(p.target + base, GPC * N * sizeof(float));
+          env.prefetch_l2(p.target + base + HALF * N, GPC * N * sizeof(float));
+        }
+      }
+    });
+  }
 
   // ---------------- P2: column FFTs + spectrum statistics ----------------
   for (int pass = 0; pass < PASSES; ++pass) {
@@ -135,7 +171,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
 #pragma unroll
         for (int e = 0; e < R1 / 2; ++e) {
           const int rr = idx_in<Cfg>(t, e);
-          const float2 zv = S[off0 + rr], zw = S[off1 + rr];
+          const float2 zv = S[off0 + IS * rr], zw = S[off1 + IS * rr];
           r.v[e] = make_float2(zv.x, zw.x);
           r.v[e + R1 / 2] = make_float2(zv.y, zw.y);
         }
@@ -143,9 +179,10 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
 #pragma unroll
         for (int e = 0; e < R1 / 2; ++e) {
           const int rr = idx_in<Cfg>(t, e);
-          const float2 zv = S[off0 + rr], zw = S[off1 + rr];
-          r.v[e] = make_float2(0.5f * (zv.x + zw.x), 0.5f * (zv.y - zw.y));
-          r.v[e + R1 / 2] = make_float2(0.5f * (zv.y + zw.y), 0.5f * (zw.x - zv.x));
+          const float2 zv = S[off0 + IS * rr], zw = S[off1 + IS * rr];
+          // 0.5 (zv + conj zw) and 0.5 (zv - conj zw) / i, as packed operations
+          r.v[e] = pk_fma(zw, make_float2(0.5f, -0.5f), pk_mul(zv, make_float2(0.5f, 0.5f)));
+          r.v[e + R1 / 2] = pk_fma(pk_swap(zv), make_float2(0.5f, -0.5f), pk_mul(pk_swap(zw), make_float2(0.5f, 0.5f)));
         }
       }
       fwd_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
@@ -166,10 +203,16 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
 #pragma unroll
         for (int e = 0; e < R1; ++e) {
           const float2 z = r.v[e];
-          const float a2 = (z.x * z.x + z.y * z.y) * inv_nn;
-          const float f = spectrum_f(a2, p.alpha, p.log_matrix);
-          sum = fmaf(f, a2, sum);
-          mx = fmaxf(mx, f);
+          if constexpr (FAST) {                          // in units of m; converted after the last pass
+            const float mm = fmaf(z.y, z.y, z.x * z.x);
+            sum = fmaf(mm, favae_fast_sqrt(mm), sum);
+            mx = fmaxf(mx, mm);
+          } else {
+            const float a2 = (z.x * z.x + z.y * z.y) * inv_nn;
+            const float f = spectrum_f(a2, p.alpha, p.log_matrix);
+            sum = fmaf(f, a2, sum);
+            mx = fmaxf(mx, f);
+          }
         }
         r.sum = fmaf(2.0f, sum, r.sum);
         r.mx = mx;
@@ -177,16 +220,21 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
 #pragma unroll
       for (int e = 0; e < R1; ++e) {
         const int u = idx_out<Cfg>(t, e);
-        S[(u < HALF) ? off0 + u : off1 + (u - HALF)] = r.v[e];
+        S[(u < HALF) ? off0 + IS * u : off1 + IS * (u - HALF)] = r.v[e];
       }
     });
     env.sync_warp();
   }
+  env.mark(3);
   env.sync_cta();
 
   // ---------------- P3: statistics of the packed columns v = 0 and v = N/2 ----------------
   env.for_threads([&](int cta, int tid) {
     ThreadRegs<Cfg>& r = env.regs(cta, tid);
+    if constexpr (FAST) {                                // m units -> (sum f A^2, max f)
+      r.sum *= inv_nn * inv_n;
+      r.mx = favae_fast_sqrt(r.mx) * inv_n;
+    }
     if (cta == 0) {
       const int m = tid / TMAP;
       int o, off0, off1;
@@ -195,8 +243,8 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       const float2* S = env.S(cta, cta);
       for (int u = tid % TMAP; u <= HALF; u += TMAP) {
         const int un = (N - u) % N;
-        const float2 a = S[(u < HALF) ? off0 + u : off1 + (u - HALF)];
-        const float2 b = S[(un < HALF) ? off0 + un : off1 + (un - HALF)];
+        const float2 a = S[(u < HALF) ? off0 + IS * u : off1 + IS * (u - HALF)];
+        const float2 b = S[(un < HALF) ? off0 + IS * un : off1 + IS * (un - HALF)];
         const float2 d0 = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
         const float2 dn = make_float2(0.5f * (a.y + b.y), 0.5f * (b.x - a.x));
         const float mult = (u == 0 || u == HALF) ? 1.0f : 2.0f;
@@ -273,10 +321,11 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
     }
   });
   if (p.grad_pred == nullptr && p.grad_target == nullptr) {
-    env.for_threads([&](int, int) { env.cluster_arrive(); });     // S is not read again
+    env.for_threads([&](int, int) { env.cluster_arrive_relaxed(); });     // S is not read again
     return;
   }
 
+  env.mark(4);
   // ---------------- P4: weight the packed columns in place ----------------
   env.for_threads([&](int cta, int tid) {
     if (cta != 0) return;
@@ -289,8 +338,8 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
     float2* S = env.S(cta, cta);
     for (int u = tid % TMAP; u <= HALF; u += TMAP) {
       const int un = (N - u) % N;
-      const int ia = (u < HALF) ? off0 + u : off1 + (u - HALF);
-      const int ib = (un < HALF) ? off0 + un : off1 + (un - HALF);
+      const int ia = (u < HALF) ? off0 + IS * u : off1 + IS * (u - HALF);
+      const int ib = (un < HALF) ? off0 + IS * un : off1 + IS * (un - HALF);
       const float2 a = S[ia], b = S[ib];
       const float2 d0 = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
       const float2 dn = make_float2(0.5f * (a.y + b.y), 0.5f * (b.x - a.x));
@@ -304,6 +353,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
   });
   env.sync_cta();
 
+  env.mark(5);
   // ---------------- P5: weight + inverse column FFTs, re-pack into Z' ----------------
   for (int pass = 0; pass < PASSES; ++pass) {
     env.for_threads([&](int cta, int tid) {
@@ -319,15 +369,17 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
 #pragma unroll
       for (int e = 0; e < R1; ++e) {
         const int u = idx_out<Cfg>(t, e);
-        r.v[e] = S[(u < HALF) ? off0 + u : off1 + (u - HALF)];
+        r.v[e] = S[(u < HALF) ? off0 + IS * u : off1 + IS * (u - HALF)];
       }
       if (v != 0) {                                      // group 0 was weighted in place by P4
+        const float finv_m = finv * inv_n;
 #pragma unroll
         for (int e = 0; e < R1; ++e) {
           const float2 z = r.v[e];
-          const float a2 = (z.x * z.x + z.y * z.y) * inv_nn;
-          const float w = spectrum_w(spectrum_f(a2, p.alpha, p.log_matrix), finv);
-          r.v[e] = make_float2(z.x * w, z.y * w);
+          float w;
+          if constexpr (FAST) w = fminf(favae_fast_sqrt(fmaf(z.y, z.y, z.x * z.x)) * finv_m, 1.0f);
+          else w = spectrum_w(spectrum_f((z.x * z.x + z.y * z.y) * inv_nn, p.alpha, p.log_matrix), finv);
+          r.v[e] = pk_mul(z, pk_dup(w));
         }
       }
       inv_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
@@ -347,22 +399,24 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
         for (int e = 0; e < R1 / 2; ++e) {
           const int rr = idx_in<Cfg>(t, e);
           const float2 a = r.v[e], b = r.v[e + R1 / 2];
-          S[off0 + rr] = make_float2(a.x, b.x);
-          S[off1 + rr] = make_float2(a.y, b.y);
+          S[off0 + IS * rr] = make_float2(a.x, b.x);
+          S[off1 + IS * rr] = make_float2(a.y, b.y);
         }
       } else {
 #pragma unroll
         for (int e = 0; e < R1 / 2; ++e) {
           const int rr = idx_in<Cfg>(t, e);
           const float2 a = r.v[e], b = r.v[e + R1 / 2];
-          S[off0 + rr] = make_float2(a.x - b.y, a.y + b.x);
-          S[off1 + rr] = make_float2(a.x + b.y, b.x - a.y);
+          S[off0 + IS * rr] = pk_fma(pk_swap(b), make_float2(-1.0f, 1.0f), a);    // a + i b
+          S[off1 + IS * rr] = pk_fma(a, make_float2(1.0f, -1.0f), pk_swap(b));    // conj(a) + i conj(b)
         }
       }
     });
     env.sync_warp();
   }
+  env.mark(6);
   env.sync_cluster();
+  env.mark(7);
 
   // ---------------- P6: inverse row FFTs, S -> gradient rows ----------------
   for (int pass = 0; pass < PASSES; ++pass) {
@@ -375,10 +429,14 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       for (int e = 0; e < R1; ++e) {
         int owner, off;
         s_lookup<Cfg>(tab, idx_out<Cfg>(t, e), m, owner, off);
-        r.v[e] = env.S(cta, owner)[off + rp];
+        r.v[e] = env.S(cta, owner)[off + IS * rp];
       }
-      if (pass == PASSES - 1) env.cluster_arrive();      // last read of S: release it for the next map
+      env.mark(8);
       inv_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
+      // last read of S: release it for the next map.  inv_stage1 has consumed every loaded value, so
+      // the reads have completed and no fence is needed (a releasing arrive would also wait for the
+      // previous pass's gradient stores to drain)
+      if (pass == PASSES - 1) env.cluster_arrive_relaxed();
     });
     env.sync_warp();
     env.for_threads([&](int cta, int tid) {
@@ -398,6 +456,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       }
     });
     env.sync_warp();
+    env.mark(9);
     env.for_threads([&](int cta, int tid) {
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
       const int g = tid / TG, t = tid % TG, item = pass * NG + g;
@@ -431,6 +490,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch) {
       }
     });
     env.sync_warp();
+    env.mark(10);
   }
 }
 

@@ -32,10 +32,34 @@ template <class Cfg> struct DevEnv {
   __device__ __forceinline__ void cluster_arrive() {
     if constexpr (Cfg::C > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   }
+  // arrive without a fence: only valid when every access the peers wait for has already completed
+  __device__ __forceinline__ void cluster_arrive_relaxed() {
+#ifdef FAVAE_FFL_NO_RELAXED
+    cluster_arrive();
+#else
+    if constexpr (Cfg::C > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+#endif
+  }
   __device__ __forceinline__ void cluster_wait() {
     if constexpr (Cfg::C == 1) __syncthreads();
     else asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
+  // phase stamps for profiles/ffl_phase_timing.cu (compiled out of the library)
+  __device__ __forceinline__ void mark(int k) {
+#ifdef FAVAE_FFL_TIMING
+    if (threadIdx.x == 0) {
+      const long long t = clock64();
+      if (k >= 0) phase_acc[k] += t - phase_last;
+      phase_last = t;
+    }
+#else
+    (void)k;
+#endif
+  }
+#ifdef FAVAE_FFL_TIMING
+  long long* phase_acc;
+  long long phase_last;
+#endif
   __device__ __forceinline__ ThreadRegs<Cfg>& regs(int, int) { return r; }
   __device__ __forceinline__ float2* S(int, int owner) {
     if constexpr (Cfg::C == 1) return s_;
@@ -49,6 +73,11 @@ template <class Cfg> struct DevEnv {
     if constexpr (Cfg::C == 1) return base;
     else return (owner == rank_) ? base : cg::this_cluster().map_shared_rank(base, owner);
   }
+  __device__ __forceinline__ void prefetch_l2(const void* ptr, size_t bytes) {
+#ifndef FAVAE_FFL_NO_L2PF
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"((unsigned)bytes) : "memory");
+#endif
+  }
   __device__ __forceinline__ float2 twiddle(int j, int n) {
     float s, c;
     sincospif(-2.0f * (float)j / (float)n, &s, &c);
@@ -56,7 +85,11 @@ template <class Cfg> struct DevEnv {
   }
 };
 
-template <class Cfg>
+#ifdef FAVAE_FFL_TIMING
+__device__ long long favae_ffl_phase_cycles[16 * 1024];
+#endif
+
+template <class Cfg, bool FAST>
 __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 256 && Cfg::SMEM_BYTES < 110 * 1024) ? 2 : 1)
 ffl_kernel(const FflParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -67,17 +100,28 @@ ffl_kernel(const FflParams p) {
   env.tab_ = reinterpret_cast<unsigned int*>(env.fb_ + 4 * Cfg::THREADS + 8 * Cfg::MPC + 8 * Cfg::C);
   if constexpr (Cfg::C == 1) env.rank_ = 0;
   else env.rank_ = (int)cg::this_cluster().block_rank();
+#ifdef FAVAE_FFL_TIMING
+  __shared__ long long phase_acc_s[16];
+  if (threadIdx.x < 16) phase_acc_s[threadIdx.x] = 0;
+  env.phase_acc = phase_acc_s;
+  env.phase_last = 0;
+#endif
   ffl_init_thread<Cfg>(env);
   env.cluster_arrive();                          // opens the split barrier the first batch waits on
   const long long batches = (p.maps + Cfg::MPC - 1) / Cfg::MPC;
   const long long stride = gridDim.x / Cfg::C;
-  for (long long b = blockIdx.x / Cfg::C; b < batches; b += stride) ffl_map_batch<Cfg>(env, p, b);
+  for (long long b = blockIdx.x / Cfg::C; b < batches; b += stride)
+    ffl_map_batch<Cfg, FAST>(env, p, b, b + stride < batches ? b + stride : -1);
   env.cluster_wait();                            // nobody leaves while a peer may still read its S
+#ifdef FAVAE_FFL_TIMING
+  __syncthreads();
+  if (threadIdx.x < 16) favae_ffl_phase_cycles[blockIdx.x * 16 + threadIdx.x] = phase_acc_s[threadIdx.x];
+#endif
 }
 
-template <class Cfg> static int launch_ffl(const FflParams& p, cudaStream_t stream) {
+template <class Cfg, bool FAST> static int launch_ffl_impl(const FflParams& p, cudaStream_t stream) {
   static bool configured = false;
-  auto kern = ffl_kernel<Cfg>;
+  auto kern = ffl_kernel<Cfg, FAST>;
   if (!configured) {
     FAVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Cfg::SMEM_BYTES));
@@ -115,6 +159,12 @@ template <class Cfg> static int launch_ffl(const FflParams& p, cudaStream_t stre
   cfg.gridDim = dim3((unsigned)(clusters * Cfg::C));
   FAVAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
   return check_launch("ffl_kernel");
+}
+
+// alpha == 1 without log weighting (every call site of the reference) takes the lean statistics path
+template <class Cfg> static int launch_ffl(const FflParams& p, cudaStream_t stream) {
+  return (p.alpha == 1.0f && !p.log_matrix) ? launch_ffl_impl<Cfg, true>(p, stream)
+                                            : launch_ffl_impl<Cfg, false>(p, stream);
 }
 
 }  // namespace favae

@@ -31,7 +31,10 @@ template <class Cfg> struct HostEnv {
   void sync_cta() {}
   void sync_cluster() {}
   void cluster_arrive() {}
+  void cluster_arrive_relaxed() {}
   void cluster_wait() {}
+  void mark(int) {}
+  void prefetch_l2(const void*, size_t) {}
   ThreadRegs<Cfg>& regs(int cta, int tid) { return regs_[cta * Cfg::THREADS + tid]; }
   float2* S(int, int owner) { return S_.data() + (size_t)owner * Cfg::S_FLOAT2; }
   float2* stg(int cta) { return stg_.data() + (size_t)cta * (Cfg::STG_FLOAT2 + 2); }
@@ -48,7 +51,11 @@ template <class Cfg> static void run(const FflParams& p) {
   HostEnv<Cfg> env;
   ffl_init_thread<Cfg>(env);
   const long long batches = (p.maps + Cfg::MPC - 1) / Cfg::MPC;
-  for (long long b = 0; b < batches; ++b) ffl_map_batch<Cfg>(env, p, b);
+  const bool fast = p.alpha == 1.0f && !p.log_matrix;     // same dispatch as ffl_kernels.cu
+  for (long long b = 0; b < batches; ++b) {
+    if (fast) ffl_map_batch<Cfg, true>(env, p, b);
+    else ffl_map_batch<Cfg, false>(env, p, b);
+  }
 }
 
 extern "C" int ffl_emul(int n, const float* pred, const float* target, long long maps, float alpha,
