@@ -255,19 +255,6 @@ FAVAE_HD float spectrum_f(float a2, float alpha, int log_matrix) {
 FAVAE_HD float spectrum_inv(float fmax) { return fmax > 0.0f ? 1.0f / fmax : 0.0f; }
 FAVAE_HD float spectrum_w(float f, float inv) { return fminf(fmaxf(f * inv, 0.0f), 1.0f); }
 
-// packed S address of map column w: owner CTA in the top byte, float2 offset of row 0 below
-template <class Cfg> FAVAE_HD unsigned int s_pack(int w) {
-  int owner, off;
-  s_locate<Cfg>(w, 0, owner, off);
-  return ((unsigned int)owner << 24) | (unsigned int)off;
-}
-template <class Cfg> FAVAE_HD void s_lookup(const unsigned int* tab, int w, int slot_map, int& owner, int& off) {
-  constexpr int GPC = Cfg::HALF / Cfg::C;
-  const unsigned int e = tab[w];
-  owner = (int)(e >> 24);
-  off = (int)(e & 0xFFFFFFu) + (Cfg::S_ENTRY_MAJOR ? 0 : slot_map * (GPC * 2 * Cfg::COLSTRIDE));
-}
-
 // ----------------------------------------------------------------------------------
 // 1-D FFT stages.  stg points at this group's staging area (R1 * STG_STRIDE float2).
 // ----------------------------------------------------------------------------------

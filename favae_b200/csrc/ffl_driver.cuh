@@ -10,7 +10,11 @@
 //   env.fbuf(cta)        float scratch: [0,2T) thread partials, [2T,4T) lane partials,
 //                        [4T, 4T+8*MPC) per-map results, then 8*C cluster slots
 //   env.cl(cta, owner)   float* to the cluster slots of CTA `owner`
-//   env.tab(cta)         N packed S addresses (s_pack), built by ffl_init_thread
+//   env.tab(cta)         per map column w: env.s_entry(cta, owner, off), the S address of entry 0 of
+//                        that column in whatever form env.s_put / env.s_get take (the device uses
+//                        32-bit shared::cluster addresses, so a row-FFT lane reaches either CTA with
+//                        one table load and one add); built by ffl_init_thread
+//   env.s_put(cta, entry, at, v) / env.s_get(cta, entry, at)   S[column of entry][at] across the cluster
 //   env.twiddle(j, n)    e^{-2 pi i j / n}
 //   env.prefetch_l2(ptr, bytes)   hint: bring a 16-byte-aligned global range into L2
 #pragma once
@@ -27,7 +31,11 @@ FAVAE_HD void ffl_init_thread(Env& env) {
 #pragma unroll
     for (int k1 = 0; k1 < Cfg::R1; ++k1) r.tw[k1] = env.twiddle(t * k1, Cfg::N);
     unsigned int* tab = env.tab(cta);
-    for (int w = tid; w < Cfg::N; w += Cfg::THREADS) tab[w] = s_pack<Cfg>(w);
+    for (int w = tid; w < Cfg::N; w += Cfg::THREADS) {
+      int owner, off;
+      s_locate<Cfg>(w, 0, owner, off);
+      tab[w] = env.s_entry(cta, owner, off);
+    }
   });
   env.sync_cta();
 }
@@ -125,12 +133,9 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       // before anybody overwrites S: the wait half of the split barrier sits here, after this
       // map's loads and row FFTs
       if (pass == 0) env.cluster_wait();
+      const int at = IS * rp + (Cfg::S_ENTRY_MAJOR ? 0 : m * (GPC * 2 * Cfg::COLSTRIDE));
 #pragma unroll
-      for (int e = 0; e < R1; ++e) {
-        int owner, off;
-        s_lookup<Cfg>(tab, idx_out<Cfg>(t, e), m, owner, off);
-        env.S(cta, owner)[off + IS * rp] = r.v[e];
-      }
+      for (int e = 0; e < R1; ++e) env.s_put(cta, tab[idx_out<Cfg>(t, e)], at, r.v[e]);
     });
     env.sync_warp();
     env.mark(1);
@@ -175,6 +180,9 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
           r.v[e] = make_float2(zv.x, zw.x);
           r.v[e + R1 / 2] = make_float2(zv.y, zw.y);
         }
+        // (stage 1 sits inside both branches: they merge after the values have gone to staging,
+        // not through two dozen register copies)
+        fwd_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
       } else {                                           // separate the two packed real rows
 #pragma unroll
         for (int e = 0; e < R1 / 2; ++e) {
@@ -184,8 +192,8 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
           r.v[e] = pk_fma(zw, make_float2(0.5f, -0.5f), pk_mul(zv, make_float2(0.5f, 0.5f)));
           r.v[e + R1 / 2] = pk_fma(pk_swap(zv), make_float2(0.5f, -0.5f), pk_mul(pk_swap(zw), make_float2(0.5f, 0.5f)));
         }
+        fwd_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
       }
-      fwd_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
     });
     env.sync_warp();
     env.for_threads([&](int cta, int tid) {
@@ -425,12 +433,9 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       const int g = tid / TG, t = tid % TG, item = pass * NG + g;
       const int m = item / GPC, rp = cta * GPC + item % GPC;
       const unsigned int* tab = env.tab(cta);
+      const int at = IS * rp + (Cfg::S_ENTRY_MAJOR ? 0 : m * (GPC * 2 * Cfg::COLSTRIDE));
 #pragma unroll
-      for (int e = 0; e < R1; ++e) {
-        int owner, off;
-        s_lookup<Cfg>(tab, idx_out<Cfg>(t, e), m, owner, off);
-        r.v[e] = env.S(cta, owner)[off + IS * rp];
-      }
+      for (int e = 0; e < R1; ++e) r.v[e] = env.s_get(cta, tab[idx_out<Cfg>(t, e)], at);
       env.mark(8);
       inv_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
       // last read of S: release it for the next map.  inv_stage1 has consumed every loaded value, so

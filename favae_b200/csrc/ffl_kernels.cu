@@ -65,6 +65,28 @@ template <class Cfg> struct DevEnv {
     if constexpr (Cfg::C == 1) return s_;
     else return (owner == rank_) ? s_ : cg::this_cluster().map_shared_rank(s_, owner);
   }
+  // S addresses for the row-FFT scatter / gather: float2 index (one CTA) or the 32-bit
+  // shared::cluster byte address of the column inside its owner CTA (clusters)
+  __device__ __forceinline__ unsigned int s_entry(int, int owner, int off) {
+    if constexpr (Cfg::C == 1) return (unsigned int)off;
+    else {
+      unsigned int local = (unsigned int)__cvta_generic_to_shared(s_ + off), remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(owner));
+      return remote;
+    }
+  }
+  __device__ __forceinline__ void s_put(int, unsigned int e, int at, float2 v) {
+    if constexpr (Cfg::C == 1) s_[e + at] = v;
+    else asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(e + 8u * (unsigned int)at), "f"(v.x), "f"(v.y) : "memory");
+  }
+  __device__ __forceinline__ float2 s_get(int, unsigned int e, int at) {
+    if constexpr (Cfg::C == 1) return s_[e + at];
+    else {
+      float2 v;
+      asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(e + 8u * (unsigned int)at) : "memory");
+      return v;
+    }
+  }
   __device__ __forceinline__ float2* stg(int) { return stg_; }
   __device__ __forceinline__ float* fbuf(int) { return fb_; }
   __device__ __forceinline__ unsigned int* tab(int) { return tab_; }

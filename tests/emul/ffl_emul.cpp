@@ -34,6 +34,9 @@ template <class Cfg> struct HostEnv {
   void cluster_arrive_relaxed() {}
   void cluster_wait() {}
   void mark(int) {}
+  unsigned int s_entry(int, int owner, int off) { return ((unsigned int)owner << 24) | (unsigned int)off; }
+  void s_put(int cta, unsigned int e, int at, float2 v) { S(cta, (int)(e >> 24))[(int)(e & 0xFFFFFFu) + at] = v; }
+  float2 s_get(int cta, unsigned int e, int at) { return S(cta, (int)(e >> 24))[(int)(e & 0xFFFFFFu) + at]; }
   void prefetch_l2(const void*, size_t) {}
   ThreadRegs<Cfg>& regs(int cta, int tid) { return regs_[cta * Cfg::THREADS + tid]; }
   float2* S(int, int owner) { return S_.data() + (size_t)owner * Cfg::S_FLOAT2; }
