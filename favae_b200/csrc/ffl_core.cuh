@@ -189,6 +189,9 @@ template <int N_, int C_, int MPC_, int THREADS_> struct FflCfg {
   static constexpr size_t SMEM_BYTES =
       sizeof(float2) * (size_t)(S_FLOAT2 + STG_FLOAT2) + sizeof(float) * (size_t)(4 * THREADS + 8 * MPC + 8 * C) + sizeof(unsigned int) * (size_t)N;
   static constexpr int IO_V4 = N / (4 * TG);       // float4 per thread and input row
+  // Issue the next batch's first loads under the current batch's last stores.  Measured on B200 for
+  // N = 256: the 64 extra live registers spill inside the row FFT (1.39 -> 1.62 ms), so it stays off.
+  static constexpr bool PIPELINE_LOADS = false;
   // I/O staging of a row pair (N float2): elements with (c % 4) < 2 in [0, N/2), the others from
   // IO_B2 on; the 8-slot shift keeps the strided float2 reads of the two halves on different banks
   static constexpr int IO_B2 = N / 2 + 8;
@@ -199,6 +202,9 @@ template <int N_, int C_, int MPC_, int THREADS_> struct FflCfg {
 template <class Cfg> struct ThreadRegs {
   float2 v[Cfg::R1];        // FFT payload
   float2 tw[Cfg::R1];       // W_N^(t*k1), forward sign
+  // the row pair in flight from HBM: pred / target, rows r' and r' + N/2.  Pass 0 of the next
+  // batch is issued before the last gradient stores of the current one
+  float4 pa[Cfg::IO_V4], ta[Cfg::IO_V4], pb[Cfg::IO_V4], tb[Cfg::IO_V4];
   float sum, mx;            // running stats
 };
 

@@ -40,7 +40,36 @@ FAVAE_HD void ffl_init_thread(Env& env) {
   env.sync_cta();
 }
 
-// One batch = MPC maps (C == 1) or one map shared by the C CTAs of a cluster.
+// Issue the HBM loads of one P1 pass (pred / target rows r', r' + N/2 of every thread group) into
+// ThreadRegs; nothing waits for them here.
+template <class Cfg, class Env>
+FAVAE_HD void ffl_issue_loads(Env& env, const FflParams& p, long long batch, int pass) {
+  constexpr int N = Cfg::N, TG = Cfg::TG, NG = Cfg::NG, HALF = Cfg::HALF, V4 = Cfg::IO_V4;
+  constexpr int GPC = HALF / Cfg::C;
+  env.for_threads([&](int cta, int tid) {
+    ThreadRegs<Cfg>& r = env.regs(cta, tid);
+    const int g = tid / TG, t = tid % TG, item = pass * NG + g;
+    const int m = item / GPC, rp = cta * GPC + item % GPC;
+    const long long map = batch * Cfg::MPC + m;
+    const bool live = map < p.maps;
+    const long long base = map * (long long)(N * N) + rp * N;
+#pragma unroll
+    for (int j = 0; j < V4; ++j) {
+      const int f = t + TG * j;                          // float4 index inside the row
+      r.pa[j] = r.ta[j] = r.pb[j] = r.tb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        r.pa[j] = *reinterpret_cast<const float4*>(p.pred + base + 4 * f);
+        r.ta[j] = *reinterpret_cast<const float4*>(p.target + base + 4 * f);
+        r.pb[j] = *reinterpret_cast<const float4*>(p.pred + base + HALF * N + 4 * f);
+        r.tb[j] = *reinterpret_cast<const float4*>(p.target + base + HALF * N + 4 * f);
+      }
+    }
+  });
+}
+
+// One batch = MPC maps (C == 1) or one map shared by the C CTAs of a cluster.  With
+// Cfg::PIPELINE_LOADS, pass 0 of its loads must already be in flight (ffl_issue_loads(batch, 0)) and
+// the batch issues pass 0 of next_batch under its last gradient stores.
 // FAST: the reference's configuration (alpha == 1, no log weighting), where f(A) = A = sqrt(m)/N with
 // m = |D|^2 unnormalised.  The spectrum statistics then run on m (sum m*sqrt(m), max m: the maximum
 // commutes with the monotone f) and are converted once per thread, and the weight is
@@ -70,27 +99,12 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
   constexpr int V4 = Cfg::IO_V4;
   constexpr int IOB4 = Cfg::IO_B2 / 2;          // float4 index of the second half of the I/O staging
   for (int pass = 0; pass < PASSES; ++pass) {
+    if (pass > 0 || !Cfg::PIPELINE_LOADS) ffl_issue_loads<Cfg>(env, p, batch, pass);
     env.for_threads([&](int cta, int tid) {
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
-      const int g = tid / TG, t = tid % TG, item = pass * NG + g;
-      const int m = item / GPC, rp = cta * GPC + item % GPC;
-      const long long map = map0 + m;
-      const bool live = map < p.maps;
-      const long long base = map * (long long)(N * N) + rp * N;
+      const int g = tid / TG, t = tid % TG;
       float4* stg4 = reinterpret_cast<float4*>(env.stg(cta) + g * STG);
-      // all 4*V4 loads are issued before the first use: one HBM round trip per pass
-      float4 pa[V4], ta[V4], pb[V4], tb[V4];
-#pragma unroll
-      for (int j = 0; j < V4; ++j) {
-        const int f = t + TG * j;                        // float4 index inside the row
-        pa[j] = ta[j] = pb[j] = tb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) {
-          pa[j] = *reinterpret_cast<const float4*>(p.pred + base + 4 * f);
-          ta[j] = *reinterpret_cast<const float4*>(p.target + base + 4 * f);
-          pb[j] = *reinterpret_cast<const float4*>(p.pred + base + HALF * N + 4 * f);
-          tb[j] = *reinterpret_cast<const float4*>(p.target + base + HALF * N + 4 * f);
-        }
-      }
+      const float4 (&pa)[V4] = r.pa, (&ta)[V4] = r.ta, (&pb)[V4] = r.pb, (&tb)[V4] = r.tb;
 #pragma unroll
       for (int j = 0; j < V4; ++j) {
         const int f = t + TG * j;
@@ -281,7 +295,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       fb[3 * T + tid] = mx;
     }
   });
-  env.sync_cta();
+  env.sync_warp();                               // the L partial sums of a map slot sit in one warp
   env.for_threads([&](int cta, int tid) {
     float* fb = env.fbuf(cta);
     const int m = tid / TMAP, j = tid % TMAP;
@@ -305,31 +319,32 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
     }
   });
   env.sync_cluster();
-  env.for_threads([&](int cta, int tid) {
-    float* fb = env.fbuf(cta);
-    if (C > 1 && tid == 0) {
+  // per-map results: (sum f A^2, max used for the weights, max of this map, 1 / used max).  Clusters
+  // combine the per-CTA slots on the fly (a few broadcast loads) instead of a third barrier.
+  auto map_stats = [&](int cta, int m, float& s, float& used, float& mx, float& finv) {
+    if constexpr (C == 1) {
+      const float* fb = env.fbuf(cta);
+      s = fb[4 * T + 2 * m]; used = fb[4 * T + 2 * m + 1]; mx = fb[4 * T + 2 * MPC + m]; finv = fb[4 * T + 3 * MPC + m];
+    } else {
       const float* cl = env.cl(cta, cta);
-      float s = 0.f, mx = 0.f;
+      s = 0.f; mx = 0.f;
       for (int o = 0; o < C; ++o) { s += cl[2 * o]; mx = fmaxf(mx, cl[2 * o + 1]); }
-      fb[4 * T] = s;
-      const float used = p.fmax_override ? p.fmax_override[0] : mx;
-      fb[4 * T + 1] = used;
-      fb[4 * T + 2 * MPC] = mx;
-      fb[4 * T + 3 * MPC] = spectrum_inv(used);
+      used = p.fmax_override ? p.fmax_override[0] : mx;
+      finv = spectrum_inv(used);
     }
-  });
-  if (C > 1) env.sync_cta();
+  };
   env.for_threads([&](int cta, int tid) {
-    const float* fb = env.fbuf(cta);
     const int m = tid / TMAP, j = tid % TMAP;
     if (cta == 0 && j == 0 && map0 + m < p.maps) {
-      const float s = fb[4 * T + 2 * m], mx = fb[4 * T + 2 * m + 1];
-      p.map_loss[map0 + m] = (mx > 0.0f) ? s / mx : 0.0f;
-      if (p.map_max) p.map_max[map0 + m] = fb[4 * T + 2 * MPC + m];
+      float s, used, mx, finv;
+      map_stats(cta, m, s, used, mx, finv);
+      p.map_loss[map0 + m] = (used > 0.0f) ? s / used : 0.0f;
+      if (p.map_max) p.map_max[map0 + m] = mx;
     }
   });
   if (p.grad_pred == nullptr && p.grad_target == nullptr) {
     env.for_threads([&](int, int) { env.cluster_arrive_relaxed(); });     // S is not read again
+    if (Cfg::PIPELINE_LOADS && next_batch >= 0) ffl_issue_loads<Cfg>(env, p, next_batch, 0);
     return;
   }
 
@@ -337,9 +352,9 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
   // ---------------- P4: weight the packed columns in place ----------------
   env.for_threads([&](int cta, int tid) {
     if (cta != 0) return;
-    const float* fb = env.fbuf(cta);
     const int m = tid / TMAP;
-    const float finv = fb[4 * T + 3 * MPC + m];
+    float s_, used_, mx_, finv;
+    map_stats(cta, m, s_, used_, mx_, finv);
     int o, off0, off1;
     s_locate<Cfg>(0, m, o, off0);
     s_locate<Cfg>(HALF, m, o, off1);
@@ -353,8 +368,8 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       const float2 dn = make_float2(0.5f * (a.y + b.y), 0.5f * (b.x - a.x));
       const float a0 = (d0.x * d0.x + d0.y * d0.y) * inv_nn;
       const float an = (dn.x * dn.x + dn.y * dn.y) * inv_nn;
-      const float w0 = spectrum_w(spectrum_f(a0, p.alpha, p.log_matrix), finv);
-      const float wn = spectrum_w(spectrum_f(an, p.alpha, p.log_matrix), finv);
+      const float w0 = spectrum_w(spectrum_f(a0, p.alpha, p.log_matrix), finv) * p.grad_scale;
+      const float wn = spectrum_w(spectrum_f(an, p.alpha, p.log_matrix), finv) * p.grad_scale;
       S[ia] = make_float2(w0 * d0.x - wn * dn.y, w0 * d0.y + wn * dn.x);
       if (ib != ia) S[ib] = make_float2(w0 * d0.x + wn * dn.y, wn * dn.x - w0 * d0.y);
     }
@@ -366,10 +381,10 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
   for (int pass = 0; pass < PASSES; ++pass) {
     env.for_threads([&](int cta, int tid) {
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
-      const float* fb = env.fbuf(cta);
       const int g = tid / TG, t = tid % TG, item = pass * NG + g;
       const int m = item / GPC, v = cta * GPC + item % GPC;
-      const float finv = fb[4 * T + 3 * MPC + m];
+      float s_, used_, mx_, finv;
+      map_stats(cta, m, s_, used_, mx_, finv);
       int o0, o1, off0, off1;
       s_locate<Cfg>(v == 0 ? 0 : v, m, o0, off0);
       s_locate<Cfg>(v == 0 ? HALF : N - v, m, o1, off1);
@@ -380,13 +395,14 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
         r.v[e] = S[(u < HALF) ? off0 + IS * u : off1 + IS * (u - HALF)];
       }
       if (v != 0) {                                      // group 0 was weighted in place by P4
-        const float finv_m = finv * inv_n;
+        // the gradient scale rides on the weights (FAST: grad_scale >= 0, so it commutes with the clamp)
+        const float gs = p.grad_scale, finv_g = finv * inv_n * gs;
 #pragma unroll
         for (int e = 0; e < R1; ++e) {
           const float2 z = r.v[e];
           float w;
-          if constexpr (FAST) w = fminf(favae_fast_sqrt(fmaf(z.y, z.y, z.x * z.x)) * finv_m, 1.0f);
-          else w = spectrum_w(spectrum_f((z.x * z.x + z.y * z.y) * inv_nn, p.alpha, p.log_matrix), finv);
+          if constexpr (FAST) w = fminf(favae_fast_sqrt(fmaf(z.y, z.y, z.x * z.x)) * finv_g, gs);
+          else w = spectrum_w(spectrum_f((z.x * z.x + z.y * z.y) * inv_nn, p.alpha, p.log_matrix), finv) * gs;
           r.v[e] = pk_mul(z, pk_dup(w));
         }
       }
@@ -462,6 +478,8 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
     });
     env.sync_warp();
     env.mark(9);
+    // the next batch's first rows start their trip from HBM / L2 under this pass's gradient stores
+    if (Cfg::PIPELINE_LOADS && pass == PASSES - 1 && next_batch >= 0) ffl_issue_loads<Cfg>(env, p, next_batch, 0);
     env.for_threads([&](int cta, int tid) {
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
       const int g = tid / TG, t = tid % TG, item = pass * NG + g;
@@ -470,18 +488,17 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       if (map < p.maps) {
         const long long base = map * (long long)(N * N) + rp * N;
         const float4* stg4 = reinterpret_cast<const float4*>(env.stg(cta) + g * STG);
-        const float gs = p.grad_scale;
 #pragma unroll
         for (int j = 0; j < V4; ++j) {
           const int f = t + TG * j;
-          float4 a, b;
+          float4 a, b;                                   // already scaled: grad_scale rode on the weights
           if constexpr (Cfg::R2 > 1) {
             const float4 lo = stg4[f], hi = stg4[IOB4 + f];
-            a = make_float4(lo.x * gs, lo.z * gs, hi.x * gs, hi.z * gs);
-            b = make_float4(lo.y * gs, lo.w * gs, hi.y * gs, hi.w * gs);
+            a = make_float4(lo.x, lo.z, hi.x, hi.z);
+            b = make_float4(lo.y, lo.w, hi.y, hi.w);
           } else {
-            a = make_float4(r.v[4 * j].x * gs, r.v[4 * j + 1].x * gs, r.v[4 * j + 2].x * gs, r.v[4 * j + 3].x * gs);
-            b = make_float4(r.v[4 * j].y * gs, r.v[4 * j + 1].y * gs, r.v[4 * j + 2].y * gs, r.v[4 * j + 3].y * gs);
+            a = make_float4(r.v[4 * j].x, r.v[4 * j + 1].x, r.v[4 * j + 2].x, r.v[4 * j + 3].x);
+            b = make_float4(r.v[4 * j].y, r.v[4 * j + 1].y, r.v[4 * j + 2].y, r.v[4 * j + 3].y);
           }
           if (p.grad_pred) {
             *reinterpret_cast<float4*>(p.grad_pred + base + 4 * f) = a;

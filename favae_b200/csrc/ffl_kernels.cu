@@ -132,7 +132,9 @@ ffl_kernel(const FflParams p) {
   env.cluster_arrive();                          // opens the split barrier the first batch waits on
   const long long batches = (p.maps + Cfg::MPC - 1) / Cfg::MPC;
   const long long stride = gridDim.x / Cfg::C;
-  for (long long b = blockIdx.x / Cfg::C; b < batches; b += stride)
+  const long long first = blockIdx.x / Cfg::C;
+  if (Cfg::PIPELINE_LOADS && first < batches) ffl_issue_loads<Cfg>(env, p, first, 0);
+  for (long long b = first; b < batches; b += stride)
     ffl_map_batch<Cfg, FAST>(env, p, b, b + stride < batches ? b + stride : -1);
   env.cluster_wait();                            // nobody leaves while a peer may still read its S
 #ifdef FAVAE_FFL_TIMING
@@ -185,8 +187,8 @@ template <class Cfg, bool FAST> static int launch_ffl_impl(const FflParams& p, c
 
 // alpha == 1 without log weighting (every call site of the reference) takes the lean statistics path
 template <class Cfg> static int launch_ffl(const FflParams& p, cudaStream_t stream) {
-  return (p.alpha == 1.0f && !p.log_matrix) ? launch_ffl_impl<Cfg, true>(p, stream)
-                                            : launch_ffl_impl<Cfg, false>(p, stream);
+  return (p.alpha == 1.0f && !p.log_matrix && p.grad_scale >= 0.0f) ? launch_ffl_impl<Cfg, true>(p, stream)
+                                                                    : launch_ffl_impl<Cfg, false>(p, stream);
 }
 
 }  // namespace favae

@@ -54,10 +54,12 @@ template <class Cfg> static void run(const FflParams& p) {
   HostEnv<Cfg> env;
   ffl_init_thread<Cfg>(env);
   const long long batches = (p.maps + Cfg::MPC - 1) / Cfg::MPC;
-  const bool fast = p.alpha == 1.0f && !p.log_matrix;     // same dispatch as ffl_kernels.cu
+  const bool fast = p.alpha == 1.0f && !p.log_matrix && p.grad_scale >= 0.0f;     // same dispatch as ffl_kernels.cu
+  if (Cfg::PIPELINE_LOADS && batches > 0) ffl_issue_loads<Cfg>(env, p, 0, 0);
   for (long long b = 0; b < batches; ++b) {
-    if (fast) ffl_map_batch<Cfg, true>(env, p, b);
-    else ffl_map_batch<Cfg, false>(env, p, b);
+    const long long nb = b + 1 < batches ? b + 1 : -1;
+    if (fast) ffl_map_batch<Cfg, true>(env, p, b, nb);
+    else ffl_map_batch<Cfg, false>(env, p, b, nb);
   }
 }
 
