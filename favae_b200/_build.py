@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'build')
-LIB = os.path.join(HERE, 'libfavae_b200.so')
+LIB = os.environ.get('FAVAE_B200_LIB') or os.path.join(HERE, 'libfavae_b200.so')   # override: experiments only
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
@@ -48,6 +48,8 @@ STAMP = os.path.join(HERE, 'libfavae_b200.stamp')
 def needs_build():
     """True unless the library exists and was built from exactly the current sources.  A content
     digest (not mtimes) decides, so a copied tree (gpurun snapshot) never triggers a rebuild."""
+    if os.environ.get('FAVAE_B200_LIB'):
+        return False                       # an explicitly named library is used as it is
     if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
     try:

@@ -15,6 +15,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "ffl_core.cuh"   // packed fp32x2 helpers (pk_add / pk_mul / pk_fma / pk_dup)
 
 namespace favae {
 namespace blurf {
@@ -127,7 +128,7 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ aux, i
 #pragma unroll
     for (int uu = 0; uu < STEP; ++uu) {
       const int r = r0 + uu;
-      const int u = uu % RS;
+      const int u = STEP == RS ? uu : uu % RS;
       if (r >= NR) break;
       if (r + Q < NR) ring[(u + Q) % RS] = load_row(r + Q);
       const float4 xrow = xq[u % XQ];
@@ -248,6 +249,345 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ aux, i
   }
 }
 
+// MODE_ADJ_SIG rewritten around packed fp32x2 arithmetic (FADD2 / FFMA2 issue two fp32 lanes per
+// slot).  Every intermediate is carried as the pair (value filtered with k, value filtered with
+// dk/dsigma): the vertical pass accumulates (v, v') per column from the window sample broadcast
+// against the tap pair (k[t], k'[t]); the shared line holds those pairs interleaved; the horizontal
+// pass forms (sum_t k[t] v, sum_t k[t] v') packed plus sum_t k'[t] v scalar.  The taps are symmetric,
+// so mirrored window samples are added first (P + 1 multiplies per output instead of 2P + 1).  Rows
+// at the top / bottom border differ from the symmetric stencil by at most P taps, applied as a
+// correction under a warp-uniform branch.  Same data path (register ring, double-buffered line,
+// one barrier per row), half the instructions of the scalar formulation.
+template <int KS, int TH>
+__global__ void __launch_bounds__(THREADS)
+blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux, int h, int w, long long items,
+                   int strips, const float* __restrict__ sigma, float* __restrict__ dst,
+                   float* __restrict__ partials) {
+  constexpr int P = KS / 2;
+  extern __shared__ float lines[];               // as float2: [2 buffers][groups][w + 2*LPAD]
+  __shared__ float sk[32], sdk[32];
+  __shared__ float wred[THREADS / 32];
+  float k[KS], dk[KS];
+  load_weights<KS>(sigma, sk, sdk, k, dk);
+  float2 kd[P + 1];                              // (k[t], k'[t]); tap t and tap KS-1-t are equal
+#pragma unroll
+  for (int t = 0; t <= P; ++t) kd[t] = make_float2(k[t], dk[t]);
+
+  const int tpi = w >> 2;                        // threads per item
+  const int groups = THREADS / tpi;
+  const int grp = threadIdx.x / tpi, tx = threadIdx.x % tpi;
+  const int x0 = tx * 4;
+  const int ll = w + 2 * LPAD;                   // float2 per line
+  float2* lines2 = reinterpret_cast<float2*>(lines);
+  const long long item = (long long)blockIdx.x * groups + grp;
+  const bool live = item < items;
+  const long long map = live ? item / strips : 0;
+  const int y0 = live ? (int)(item % strips) * TH : 0;
+  const float* base = src + map * (long long)h * w;
+  float acc_sigma = 0.f;
+
+  constexpr int Q = 6 + ((3 - (KS + 6) % 3) % 3), RS = KS + Q, XQ = 3, NR = TH + KS - 1;
+  static_assert(RS % XQ == 0, "x prefetch ring must tile the unroll factor");
+  const long long mapoff = map * (long long)h * w;
+  auto load_row = [&](int r) -> float4 {
+    const int yi = y0 - P + r;
+    float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) in = ld4(base + (long long)reflect_idx(yi, h) * w + x0);
+    return in;
+  };
+  auto load_x = [&](int r) -> float4 {           // x row of the output produced at iteration r
+    const int yo = y0 + r - (KS - 1);
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live && r >= KS - 1 && yo < h) xv = ld4(aux + mapoff + (long long)yo * w + x0);
+    return xv;
+  };
+  float4 ring[RS], xq[XQ];
+#pragma unroll
+  for (int q = 0; q < RS; ++q) ring[q] = (q < Q) ? load_row(q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < XQ; ++q) xq[q] = load_x(q);
+  constexpr int STEP = RS;                       // unrolling all NR rows was slower (code size)
+#pragma unroll 1
+  for (int r0 = 0; r0 < NR; r0 += STEP) {
+#pragma unroll
+    for (int uu = 0; uu < STEP; ++uu) {
+      const int r = r0 + uu;
+      const int u = STEP == RS ? uu : uu % RS;
+      if (r >= NR) break;
+      if (r + Q < NR) ring[(u + Q) % RS] = load_row(r + Q);
+      const float4 xrow = xq[u % XQ];
+      if (r + XQ < NR) xq[u % XQ] = load_x(r + XQ);
+      if (r < KS - 1) continue;
+      const int yo = y0 + r - (KS - 1);            // output row of this iteration
+#define FAVAE_WIN(t) ring[(u + RS - (KS - 1) + (t)) % RS]
+      // ---- vertical pass: acc[c] = (sum_t k[t] g, sum_t k'[t] g) over the mirrored window
+      float2 acc[4];
+      {
+        const float4& m = FAVAE_WIN(P);
+        acc[0] = pk_mul(pk_dup(m.x), kd[P]); acc[1] = pk_mul(pk_dup(m.y), kd[P]);
+        acc[2] = pk_mul(pk_dup(m.z), kd[P]); acc[3] = pk_mul(pk_dup(m.w), kd[P]);
+#pragma unroll
+        for (int t = 0; t < P; ++t) {
+          const float4& a = FAVAE_WIN(t);
+          const float4& b = FAVAE_WIN(KS - 1 - t);
+          const float2 s01 = pk_add(make_float2(a.x, a.y), make_float2(b.x, b.y));
+          const float2 s23 = pk_add(make_float2(a.z, a.w), make_float2(b.z, b.w));
+          acc[0] = pk_fma(pk_dup(s01.x), kd[t], acc[0]); acc[1] = pk_fma(pk_dup(s01.y), kd[t], acc[1]);
+          acc[2] = pk_fma(pk_dup(s23.x), kd[t], acc[2]); acc[3] = pk_fma(pk_dup(s23.y), kd[t], acc[3]);
+        }
+      }
+      // border rows of the adjoint (see the derivation above blur_fast_kernel): the border output
+      // takes no mirrored taps; outputs 1..P next to a border take the border sample once more
+      const int jrow = h - 1 - yo;
+      if (live && (yo <= P || (jrow >= 0 && jrow <= P))) {
+        auto axpy = [&](const float4& g, float2 kk) {
+          acc[0] = pk_fma(pk_dup(g.x), kk, acc[0]); acc[1] = pk_fma(pk_dup(g.y), kk, acc[1]);
+          acc[2] = pk_fma(pk_dup(g.z), kk, acc[2]); acc[3] = pk_fma(pk_dup(g.w), kk, acc[3]);
+        };
+        if (yo == 0) {
+#pragma unroll
+          for (int t = 0; t < P; ++t) axpy(FAVAE_WIN(t), make_float2(-kd[t].x, -kd[t].y));
+        }
+        if (jrow == 0) {
+#pragma unroll
+          for (int t = 0; t < P; ++t) axpy(FAVAE_WIN(KS - 1 - t), make_float2(-kd[t].x, -kd[t].y));
+        }
+        if (yo >= 1 && yo <= P) axpy(ld4(base + x0), make_float2(sk[P - yo], sdk[P - yo]));
+        if (jrow >= 1 && jrow <= P) axpy(ld4(base + (long long)(h - 1) * w + x0), make_float2(sk[P - jrow], sdk[P - jrow]));
+      }
+#undef FAVAE_WIN
+      // ---- horizontal pass through a shared line of (v, v') pairs
+      float2* line = lines2 + (size_t)((r & 1) * groups + grp) * ll;
+      *reinterpret_cast<float4*>(line + LPAD + x0) = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+      *reinterpret_cast<float4*>(line + LPAD + x0 + 2) = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+      if (tx == 0 || tx == tpi - 1 || (P > 3 && (tx == 1 || tx == tpi - 2))) {
+        // mirrored halo entries (reflect): index -j <- j, index w-1+j <- w-1-j
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int j = x0 + c;
+          if (j >= 1 && j <= P) line[LPAD - j] = acc[c];
+          const int jr = w - 1 - j;
+          if (jr >= 1 && jr <= P) line[LPAD + w - 1 + jr] = acc[c];
+        }
+      }
+      __syncthreads();
+      float2 seg[4 + 2 * P];
+      if constexpr (P % 2 == 0) {                  // LPAD + x0 - P is even: 16-byte aligned pairs of pairs
+        const float4* l4 = reinterpret_cast<const float4*>(line + LPAD + x0 - P);
+#pragma unroll
+        for (int i = 0; i < 2 + P; ++i) {
+          const float4 q = l4[i];
+          seg[2 * i] = make_float2(q.x, q.y); seg[2 * i + 1] = make_float2(q.z, q.w);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4 + 2 * P; ++i) seg[i] = line[LPAD + x0 - P + i];
+      }
+      float o[4], z[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float2 a2 = pk_mul(pk_dup(k[P]), seg[c + P]);          // (sum k v, sum k v')
+        float za = dk[P] * seg[c + P].x;                        // sum k' v
+#pragma unroll
+        for (int t = 0; t < P; ++t) {
+          const float2 q = pk_add(seg[c + t], seg[c + KS - 1 - t]);
+          a2 = pk_fma(pk_dup(k[t]), q, a2);
+          za = fmaf(dk[t], q.x, za);
+        }
+        o[c] = a2.x; z[c] = a2.y + za;
+      }
+      if (tx == 0 || (tx == 1 && P > 3)) {
+        const float2 g0 = line[LPAD];
+        if (tx == 0) {
+          o[0] = 0.f; z[0] = 0.f;                        // column 0: only the taps inside the map
+#pragma unroll
+          for (int t = P; t < KS; ++t) {
+            o[0] = fmaf(k[t], seg[t].x, o[0]);
+            z[0] = fmaf(dk[t], seg[t].x, fmaf(k[t], seg[t].y, z[0]));
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {                    // columns 1..P: the border sample itself
+          const int j = x0 + c;
+          if (j >= 1 && j <= P) {
+            o[c] = fmaf(sk[P - j], g0.x, o[c]);
+            z[c] = fmaf(sdk[P - j], g0.x, fmaf(sk[P - j], g0.y, z[c]));
+          }
+        }
+      }
+      if (tx == tpi - 1 || (tx == tpi - 2 && P > 3)) {
+        const float2 g0 = line[LPAD + w - 1];
+        if (tx == tpi - 1) {
+          o[3] = 0.f; z[3] = 0.f;
+#pragma unroll
+          for (int t = 0; t <= P; ++t) {
+            o[3] = fmaf(k[t], seg[3 + t].x, o[3]);
+            z[3] = fmaf(dk[t], seg[3 + t].x, fmaf(k[t], seg[3 + t].y, z[3]));
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int jr = w - 1 - (x0 + c);
+          if (jr >= 1 && jr <= P) {
+            o[c] = fmaf(sk[P - jr], g0.x, o[c]);
+            z[c] = fmaf(sdk[P - jr], g0.x, fmaf(sk[P - jr], g0.y, z[c]));
+          }
+        }
+      }
+      if (live && yo < h) {
+        *reinterpret_cast<float4*>(dst + mapoff + (long long)yo * w + x0) = make_float4(o[0], o[1], o[2], o[3]);
+        acc_sigma = fmaf(xrow.x, z[0], fmaf(xrow.y, z[1], fmaf(xrow.z, z[2], fmaf(xrow.w, z[3], acc_sigma))));
+      }
+    }
+  }
+  acc_sigma = warp_sum(acc_sigma);
+  if ((threadIdx.x & 31) == 0) wred[threadIdx.x >> 5] = acc_sigma;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) s += wred[i];
+    partials[blockIdx.x] = s;
+  }
+}
+
+// MODE_SIGMA with the same packed arithmetic: d/dsigma <gy, H V x> = <gy, (H'V + HV') x> on the forward
+// data path (reflect halos only, no border corrections, nothing stored): x goes through the
+// (V x, V' x) / (H ., H' .) pair pipeline of blur_adjsig_kernel and each finished row is dotted
+// with the matching gy row.  Together with MODE_ADJ this replaces the fused adjoint + sigma kernel
+// when the two lean kernels are faster than the fused one.
+// Measured on B200 (4096 maps of 256^2, k = 9, together with the plain adjoint): rolled 15-row unroll
+// at 154 registers 1.03 ms; capped at 128 registers (4 CTAs / SM) 0.85 ms; all rows unrolled 0.95 ms;
+// both 0.69 ms.
+#ifndef FAVAE_SIGMA_MINB
+#define FAVAE_SIGMA_MINB 4
+#endif
+#ifndef FAVAE_SIGMA_FULL
+#define FAVAE_SIGMA_FULL 1
+#endif
+template <int KS, int TH>
+__global__ void __launch_bounds__(THREADS, FAVAE_SIGMA_MINB)
+blur_sigma_kernel(const float* __restrict__ src, const float* __restrict__ aux, int h, int w, long long items,
+                  int strips, const float* __restrict__ sigma, float* __restrict__ partials) {
+  constexpr int P = KS / 2;
+  extern __shared__ float lines[];               // as float2: [2 buffers][groups][w + 2*LPAD]
+  __shared__ float sk[32], sdk[32];
+  __shared__ float wred[THREADS / 32];
+  float k[KS], dk[KS];
+  load_weights<KS>(sigma, sk, sdk, k, dk);
+  float2 kd[P + 1];
+#pragma unroll
+  for (int t = 0; t <= P; ++t) kd[t] = make_float2(k[t], dk[t]);
+
+  const int tpi = w >> 2;
+  const int groups = THREADS / tpi;
+  const int grp = threadIdx.x / tpi, tx = threadIdx.x % tpi;
+  const int x0 = tx * 4;
+  const int ll = w + 2 * LPAD;
+  float2* lines2 = reinterpret_cast<float2*>(lines);
+  const long long item = (long long)blockIdx.x * groups + grp;
+  const bool live = item < items;
+  const long long map = live ? item / strips : 0;
+  const int y0 = live ? (int)(item % strips) * TH : 0;
+  const float* base = src + map * (long long)h * w;
+  float acc_sigma = 0.f;
+
+  constexpr int Q = 6 + ((3 - (KS + 6) % 3) % 3), RS = KS + Q, XQ = 3, NR = TH + KS - 1;
+  static_assert(RS % XQ == 0, "gy prefetch ring must tile the unroll factor");
+  const long long mapoff = map * (long long)h * w;
+  auto load_row = [&](int r) -> float4 {
+    const int yi = y0 - P + r;
+    float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) in = ld4(base + (long long)reflect_idx(yi, h) * w + x0);
+    return in;
+  };
+  auto load_g = [&](int r) -> float4 {           // gy row of the output produced at iteration r
+    const int yo = y0 + r - (KS - 1);
+    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live && r >= KS - 1 && yo < h) gv = ld4(aux + mapoff + (long long)yo * w + x0);
+    return gv;
+  };
+  float4 ring[RS], gq[XQ];
+#pragma unroll
+  for (int q = 0; q < RS; ++q) ring[q] = (q < Q) ? load_row(q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < XQ; ++q) gq[q] = load_g(q);
+  constexpr int STEP = FAVAE_SIGMA_FULL ? NR : RS;
+#pragma unroll 1
+  for (int r0 = 0; r0 < NR; r0 += STEP) {
+#pragma unroll
+    for (int uu = 0; uu < STEP; ++uu) {
+      const int r = r0 + uu;
+      const int u = STEP == RS ? uu : uu % RS;
+      if (r >= NR) break;
+      if (r + Q < NR) ring[(u + Q) % RS] = load_row(r + Q);
+      const float4 grow = gq[u % XQ];            // zero outside the map: those rows add nothing
+      if (r + XQ < NR) gq[u % XQ] = load_g(r + XQ);
+      if (r < KS - 1) continue;
+#define FAVAE_WIN(t) ring[(u + RS - (KS - 1) + (t)) % RS]
+      float2 acc[4];
+      {
+        const float4& m = FAVAE_WIN(P);
+        acc[0] = pk_mul(pk_dup(m.x), kd[P]); acc[1] = pk_mul(pk_dup(m.y), kd[P]);
+        acc[2] = pk_mul(pk_dup(m.z), kd[P]); acc[3] = pk_mul(pk_dup(m.w), kd[P]);
+#pragma unroll
+        for (int t = 0; t < P; ++t) {
+          const float4& a = FAVAE_WIN(t);
+          const float4& b = FAVAE_WIN(KS - 1 - t);
+          const float2 s01 = pk_add(make_float2(a.x, a.y), make_float2(b.x, b.y));
+          const float2 s23 = pk_add(make_float2(a.z, a.w), make_float2(b.z, b.w));
+          acc[0] = pk_fma(pk_dup(s01.x), kd[t], acc[0]); acc[1] = pk_fma(pk_dup(s01.y), kd[t], acc[1]);
+          acc[2] = pk_fma(pk_dup(s23.x), kd[t], acc[2]); acc[3] = pk_fma(pk_dup(s23.y), kd[t], acc[3]);
+        }
+      }
+#undef FAVAE_WIN
+      float2* line = lines2 + (size_t)((r & 1) * groups + grp) * ll;
+      *reinterpret_cast<float4*>(line + LPAD + x0) = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+      *reinterpret_cast<float4*>(line + LPAD + x0 + 2) = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+      if (tx == 0 || tx == tpi - 1 || (P > 3 && (tx == 1 || tx == tpi - 2))) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int j = x0 + c;
+          if (j >= 1 && j <= P) line[LPAD - j] = acc[c];
+          const int jr = w - 1 - j;
+          if (jr >= 1 && jr <= P) line[LPAD + w - 1 + jr] = acc[c];
+        }
+      }
+      __syncthreads();
+      float2 seg[4 + 2 * P];
+      if constexpr (P % 2 == 0) {
+        const float4* l4 = reinterpret_cast<const float4*>(line + LPAD + x0 - P);
+#pragma unroll
+        for (int i = 0; i < 2 + P; ++i) {
+          const float4 q = l4[i];
+          seg[2 * i] = make_float2(q.x, q.y); seg[2 * i + 1] = make_float2(q.z, q.w);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4 + 2 * P; ++i) seg[i] = line[LPAD + x0 - P + i];
+      }
+      const float gv[4] = {grow.x, grow.y, grow.z, grow.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        // z = sum_t k'[t] v + sum_t k[t] v': the pair (k'[t], k[t]) against the pair (v, v'), summed over lanes
+        float2 a2 = pk_mul(make_float2(dk[P], k[P]), seg[c + P]);
+#pragma unroll
+        for (int t = 0; t < P; ++t) a2 = pk_fma(make_float2(dk[t], k[t]), pk_add(seg[c + t], seg[c + KS - 1 - t]), a2);
+        acc_sigma = fmaf(gv[c], a2.x + a2.y, acc_sigma);
+      }
+    }
+  }
+  acc_sigma = warp_sum(acc_sigma);
+  if ((threadIdx.x & 31) == 0) wred[threadIdx.x >> 5] = acc_sigma;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) s += wred[i];
+    partials[blockIdx.x] = s;
+  }
+}
+
 inline bool supported(int h, int w, int ks) {
   const bool pow2 = w >= 4 && w <= 512 && (w & (w - 1)) == 0;
   const bool kok = ks == 3 || ks == 5 || ks == 9 || ks == 11 || ks == 15;
@@ -267,8 +607,13 @@ static int launch_one(const float* src, const float* aux, long long maps, int h,
   const long long items = maps * strips;
   const long long blocks = (items + groups - 1) / groups;
   const size_t smem = sizeof(float) * 2 * groups * ((MODE == MODE_ADJ_SIG || MODE == MODE_SIGMA) ? 2 : 1) * (size_t)(w + 2 * LPAD);
-  blur_fast_kernel<KS, TH, MODE><<<(unsigned)blocks, THREADS, smem, s>>>(src, aux, h, w, items, strips, sigma, dst,
-                                                                      partials);
+  if constexpr (MODE == MODE_ADJ_SIG)
+    blur_adjsig_kernel<KS, TH><<<(unsigned)blocks, THREADS, smem, s>>>(src, aux, h, w, items, strips, sigma, dst, partials);
+  else if constexpr (MODE == MODE_SIGMA)
+    blur_sigma_kernel<KS, TH><<<(unsigned)blocks, THREADS, smem, s>>>(src, aux, h, w, items, strips, sigma, partials);
+  else
+    blur_fast_kernel<KS, TH, MODE><<<(unsigned)blocks, THREADS, smem, s>>>(src, aux, h, w, items, strips, sigma, dst,
+                                                                        partials);
   return check_launch("blur_fast");
 }
 
