@@ -375,15 +375,15 @@ def main():
             'clocks': clocks,
             'roofline': {'kernel': 'ffl_kernel<256> (level-0 DSL spectrum loss, 128x256x256 maps per image)',
                          'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm'], 'unit': 'GB/s',
-                         'frac': achieved / pk['hbm'], 'traffic': 15.22 * e_l0, 'peak_source': pk['src'],
-                         'traffic_source': 'ncu --set full dram__bytes_read+write = 15.22 B/element (profiles/ncu_r1_summary.md)',
+                         'frac': achieved / pk['hbm'], 'traffic': 16.64 * e_l0, 'peak_source': pk['src'],
+                         'traffic_source': 'ncu --set full dram__bytes_read+write = 16.64 B/element incl. the L2 prefetch of the next map (profiles/ncu_r1_summary.md)',
                          'algorithmic_bytes_per_launch': 16.0 * e_l0, 'ms_per_launch': l0_ms},
             'roofline_vq': {'kernel': 'favae_vq_search_tc: tcgen05 cta_group::2 search + exact re-score + fallback, '
                                       '16384 x 256 codebook; algorithmic 2*N*K*D flops',
                             'bound': 'tensor', 'peak': pk['tf'], 'unit': 'TFLOP/s', 'peak_source': pk['src'],
                             'workload': vq_line(n_lat, vq_ms), 'microbench_large_n': vq_line(big_n, vq_big_ms),
                             'achieved': vq_line(big_n, vq_big_ms)['achieved'], 'frac': vq_line(big_n, vq_big_ms)['frac']},
-            'roofline_blur': {'kernel': 'blur_fast_kernel<9,32,*> on the level-0 maps', 'bound': 'hbm',
+            'roofline_blur': {'kernel': 'blur_fast_kernel<9,32,*> (forward, adjoint) + blur_sigma_kernel<9,32> on the level-0 maps', 'bound': 'hbm',
                               'peak': pk['hbm'], 'unit': 'GB/s',
                               'forward': {'ms': blur_ms['fwd'], 'achieved': 8.0 * e_l0 / (blur_ms['fwd'] * 1e-3) / 1e9,
                                           'frac': 8.0 * e_l0 / (blur_ms['fwd'] * 1e-3) / 1e9 / pk['hbm'],

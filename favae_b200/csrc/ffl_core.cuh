@@ -190,7 +190,8 @@ template <int N_, int C_, int MPC_, int THREADS_> struct FflCfg {
       sizeof(float2) * (size_t)(S_FLOAT2 + STG_FLOAT2) + sizeof(float) * (size_t)(4 * THREADS + 8 * MPC + 8 * C) + sizeof(unsigned int) * (size_t)N;
   static constexpr int IO_V4 = N / (4 * TG);       // float4 per thread and input row
   // Issue the next batch's first loads under the current batch's last stores.  Measured on B200 for
-  // N = 256: the 64 extra live registers spill inside the row FFT (1.39 -> 1.62 ms), so it stays off.
+  // N = 256: at 512 threads the 64 extra live registers spill inside the row FFT (1.39 -> 1.62 ms);
+  // at 256 threads / 220 registers it fits but gains 1 % (1.47 -> 1.46 ms), so it stays off.
   static constexpr bool PIPELINE_LOADS = false;
   // I/O staging of a row pair (N float2): elements with (c % 4) < 2 in [0, N/2), the others from
   // IO_B2 on; the 8-slot shift keeps the strided float2 reads of the two halves on different banks
