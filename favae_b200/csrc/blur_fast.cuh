@@ -58,28 +58,32 @@ __device__ __forceinline__ void load_weights(const float* sigma_ptr, float* sk, 
   for (int t = 0; t < KS; ++t) { k[t] = sk[t]; dk[t] = sdk[t]; }
 }
 
-// Adjoint of (reflect-pad, correlate) without folding.  Writing the reflected samples explicitly,
-//   gx[j] = sum_q g[q] k[q-j+P]  +  [1 <= j <= P] sum_{o=0}^{P-j} g[o] k[P-j-o]   (+ mirror at the far border)
-// which is the FORWARD stencil on the mirrored extension of g, except that
-//   * the border sample itself (o = 0) is missing from the mirror:  gx[j] += k[P-j] g[0], 1 <= j <= P
-//   * the border output (j = 0) takes no mirrored taps at all.
-// So the adjoint reuses the forward data path (mirrored halos) plus these two O(1) corrections per
-// border, which keeps its instruction stream as short as the forward one.
-
+// Adjoint of (reflect-pad, correlate) as a FORWARD stencil.  With taps symmetric about the centre,
+//   H^T g = D (stencil on the mirrored extension of E g),   E = diag(2, 1, ..., 1, 2),  D = diag(1/2, 1, ..., 1, 1/2):
+// the reflected copies of samples 1..P land where the mirror puts them; the border sample is never
+// reflected, which the forward stencil makes up for by seeing it twice (E); and the border output,
+// which would receive every contribution twice, is halved (D).  (Checked against autograd for
+// every P < w, including P = w - 1, in tests/test_abi_and_host.py.)  The adjoint therefore runs the
+// forward data path with two scalings per border instead of per-row tap masks and corrections.
+// adjoint: rolled RS-row unroll at 128 registers (4 CTAs / SM) measured best (0.565 ms at 4096 maps
+// of 256^2; all rows unrolled 0.71 ms, 146 registers 0.63 ms, 96 registers with spills 0.67 ms)
+#ifndef FAVAE_ADJ_FULL
+#define FAVAE_ADJ_FULL 0
+#endif
+#ifndef FAVAE_ADJ_MINB
+#define FAVAE_ADJ_MINB 4
+#endif
 template <int KS, int TH, int MODE>
-__global__ void __launch_bounds__(THREADS)
-blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ aux, int h, int w, long long items,
+__global__ void __launch_bounds__(THREADS, MODE == MODE_ADJ ? FAVAE_ADJ_MINB : 5)
+blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ /*aux*/, int h, int w, long long items,
                  int strips, const float* __restrict__ sigma, float* __restrict__ dst,
-                 float* __restrict__ partials) {
-  // src: x (FWD, SIGMA) or gy (ADJ*); aux: x (ADJ_SIG) / gy (SIGMA); dst: y / gx
+                 float* __restrict__ /*partials*/) {
+  // src: x (FWD) or gy (ADJ); dst: y / gx
+  static_assert(MODE == MODE_FWD || MODE == MODE_ADJ, "sigma-gradient modes have their own kernels");
   constexpr int P = KS / 2;
-  constexpr bool ADJ = MODE == MODE_ADJ || MODE == MODE_ADJ_SIG;
-  constexpr bool SIG = MODE == MODE_ADJ_SIG || MODE == MODE_SIGMA;
-  constexpr bool STORE = MODE != MODE_SIGMA;
-  constexpr int NV = SIG ? 2 : 1;
-  extern __shared__ float lines[];               // [2 buffers][groups][NV][w + 2*LPAD]
+  constexpr bool ADJ = MODE == MODE_ADJ;
+  extern __shared__ float lines[];               // [2 buffers][groups][w + 2*LPAD]
   __shared__ float sk[32], sdk[32];
-  __shared__ float wred[THREADS / 32];
   float k[KS], dk[KS];
   load_weights<KS>(sigma, sk, sdk, k, dk);
 
@@ -93,159 +97,75 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ aux, i
   const long long map = live ? item / strips : 0;
   const int y0 = live ? (int)(item % strips) * TH : 0;
   const float* base = src + map * (long long)h * w;
-  float acc_sigma = 0.f;
+  const float e0 = (ADJ && tx == 0) ? 2.f : 1.f, e3 = (ADJ && tx == tpi - 1) ? 2.f : 1.f;   // E, columns
+  const float d0 = (ADJ && tx == 0) ? 0.5f : 1.f, d3 = (ADJ && tx == tpi - 1) ? 0.5f : 1.f; // D, columns
 
   // Register ring of RS = KS + Q rows: the KS-row window of the vertical pass plus Q rows in flight
   // from HBM (explicit prefetch: ~6 rows per thread are needed to cover the HBM latency at this
-  // occupancy).  The row loop is unrolled RS-fold so every ring index is a constant; unrolling all
-  // TH + KS - 1 rows overflows the instruction cache in the sigma-gradient variant.
-  constexpr int Q = 6 + ((3 - (KS + 6) % 3) % 3), RS = KS + Q, XQ = 3, NR = TH + KS - 1;
-  static_assert(RS % XQ == 0, "x prefetch ring must tile the unroll factor");
+  // occupancy).  All NR rows are unrolled so every ring index is a constant.
+  constexpr int Q = 6 + ((3 - (KS + 6) % 3) % 3), RS = KS + Q, NR = TH + KS - 1;
   const long long mapoff = map * (long long)h * w;
   auto load_row = [&](int r) -> float4 {
-    const int yi = y0 - P + r;
+    const int ry = reflect_idx(y0 - P + r, h);
     float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) in = ld4(base + (long long)reflect_idx(yi, h) * w + x0);
+    if (live) in = ld4(base + (long long)ry * w + x0);
     return in;
   };
-  auto load_x = [&](int r) -> float4 {           // x row of the output produced at iteration r
-    const int yo = y0 + r - (KS - 1);
-    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (SIG && live && r >= KS - 1 && yo < h) xv = ld4(aux + mapoff + (long long)yo * w + x0);
-    return xv;
-  };
-  float4 ring[RS], xq[XQ];
+  float4 ring[RS];
 #pragma unroll
   for (int q = 0; q < RS; ++q) ring[q] = (q < Q) ? load_row(q) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int q = 0; q < XQ; ++q) xq[q] = load_x(q);
-  // FULL: all rows unrolled (fastest while the code fits the instruction cache: forward and plain
-  // adjoint); otherwise RS-fold unroll inside a rolled loop (sigma-gradient variant)
-  constexpr bool FULL = MODE != MODE_ADJ_SIG;
-  constexpr int STEP = FULL ? NR : RS;
+  constexpr int STEP = (ADJ && !FAVAE_ADJ_FULL) ? RS : NR;
 #pragma unroll 1
-  for (int r0 = 0; r0 < NR; r0 += STEP) {
+  for (int r0 = 0; r0 < NR; r0 += STEP)
 #pragma unroll
-    for (int uu = 0; uu < STEP; ++uu) {
-      const int r = r0 + uu;
-      const int u = STEP == RS ? uu : uu % RS;
-      if (r >= NR) break;
-      if (r + Q < NR) ring[(u + Q) % RS] = load_row(r + Q);
-      const float4 xrow = xq[u % XQ];
-      if (SIG && r + XQ < NR) xq[u % XQ] = load_x(r + XQ);
-      if (r < KS - 1) continue;
-      const int yo = y0 + r - (KS - 1);            // output row of this iteration
-      // ---- vertical pass over the window rows yo - P .. yo + P
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f), vd = make_float4(0.f, 0.f, 0.f, 0.f);
-      const bool top = ADJ && yo == 0, bot = ADJ && yo == h - 1;   // border outputs: no mirrored taps
+  for (int uu = 0; uu < STEP; ++uu) {
+    const int r = r0 + uu;
+    const int u = STEP == RS ? uu : uu % RS;
+    if (r >= NR) break;
+    if (r + Q < NR) ring[(u + Q) % RS] = load_row(r + Q);
+    if (ADJ) {
+      // E, rows: doubled when the row enters the window (Q iterations after its load was issued:
+      // scaling at load time would make every iteration wait for the row it has just requested)
+      const int ry = reflect_idx(y0 - P + r, h);
+      if (ry == 0 || ry == h - 1) { float4& b = ring[u]; b.x *= 2.f; b.y *= 2.f; b.z *= 2.f; b.w *= 2.f; }
+    }
+    if (r < KS - 1) continue;
+    const int yo = y0 + r - (KS - 1);            // output row of this iteration
+    // ---- vertical pass over the window rows yo - P .. yo + P
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int t = 0; t < KS; ++t) {
-        const float4& wv = ring[(u + RS - (KS - 1) + t) % RS];
-        const bool drop = (t < P && top) || (t > P && bot);
-        fma4(v, drop ? 0.f : k[t], wv);
-        if (SIG) fma4(vd, drop ? 0.f : dk[t], wv);
-      }
-      if (ADJ && live) {
-        if (yo >= 1 && yo <= P) {                        // missing border sample of the mirror
-          const float4 g = ld4(base + x0);
-          fma4(v, sk[P - yo], g);
-          if (SIG) fma4(vd, sdk[P - yo], g);
-        }
-        const int jr = h - 1 - yo;
-        if (jr >= 1 && jr <= P) {
-          const float4 g = ld4(base + (long long)(h - 1) * w + x0);
-          fma4(v, sk[P - jr], g);
-          if (SIG) fma4(vd, sdk[P - jr], g);
-        }
-      }
-      // ---- horizontal pass through a shared line
-      float* line = lines + ((size_t)((r & 1) * groups + grp) * NV) * ll;
-      *reinterpret_cast<float4*>(line + LPAD + x0) = v;
-      if (SIG) *reinterpret_cast<float4*>(line + ll + LPAD + x0) = vd;
-      {
-        // mirrored halo entries (reflect): index -j <- j, index w-1+j <- w-1-j
-        const float vv[4] = {v.x, v.y, v.z, v.w}, vvd[4] = {vd.x, vd.y, vd.z, vd.w};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int j = x0 + c;
-          if (j >= 1 && j <= P) { line[LPAD - j] = vv[c]; if (SIG) line[ll + LPAD - j] = vvd[c]; }
-          const int jr = w - 1 - j;
-          if (jr >= 1 && jr <= P) { line[LPAD + w - 1 + jr] = vv[c]; if (SIG) line[ll + LPAD + w - 1 + jr] = vvd[c]; }
-        }
-      }
-      __syncthreads();
-      float seg[4 + 2 * P], segd[SIG ? 4 + 2 * P : 1];
-#pragma unroll
-      for (int i = 0; i < 4 + 2 * P; ++i) {
-        seg[i] = line[LPAD + x0 - P + i];
-        if (SIG) segd[i] = line[ll + LPAD + x0 - P + i];
-      }
-      float o[4] = {0.f, 0.f, 0.f, 0.f}, z[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < KS; ++t) fma4(v, k[t], ring[(u + RS - (KS - 1) + t) % RS]);
+    if (ADJ) { v.x *= e0; v.w *= e3; }
+    // ---- horizontal pass through a shared line
+    float* line = lines + (size_t)((r & 1) * groups + grp) * ll;
+    *reinterpret_cast<float4*>(line + LPAD + x0) = v;
+    {
+      // mirrored halo entries (reflect): index -j <- j, index w-1+j <- w-1-j
+      const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-#pragma unroll
-        for (int t = 0; t < KS; ++t) {
-          o[c] = fmaf(k[t], seg[c + t], o[c]);
-          if (SIG) z[c] = fmaf(dk[t], seg[c + t], fmaf(k[t], segd[c + t], z[c]));
-        }
-      }
-      if (ADJ) {
-        if (tx == 0 || (tx == 1 && P > 3)) {
-          const float g0 = line[LPAD], gd0 = SIG ? line[ll + LPAD] : 0.f;
-          if (tx == 0) {
-            o[0] = 0.f; z[0] = 0.f;                      // column 0: only the taps inside the map
-#pragma unroll
-            for (int t = P; t < KS; ++t) {
-              o[0] = fmaf(k[t], seg[t], o[0]);
-              if (SIG) z[0] = fmaf(dk[t], seg[t], fmaf(k[t], segd[t], z[0]));
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {                  // columns 1..P: the border sample itself
-            const int j = x0 + c;
-            if (j >= 1 && j <= P) {
-              o[c] = fmaf(sk[P - j], g0, o[c]);
-              if (SIG) z[c] = fmaf(sdk[P - j], g0, fmaf(sk[P - j], gd0, z[c]));
-            }
-          }
-        }
-        if (tx == tpi - 1 || (tx == tpi - 2 && P > 3)) {
-          const float g0 = line[LPAD + w - 1], gd0 = SIG ? line[ll + LPAD + w - 1] : 0.f;
-          if (tx == tpi - 1) {
-            o[3] = 0.f; z[3] = 0.f;
-#pragma unroll
-            for (int t = 0; t <= P; ++t) {
-              o[3] = fmaf(k[t], seg[3 + t], o[3]);
-              if (SIG) z[3] = fmaf(dk[t], seg[3 + t], fmaf(k[t], segd[3 + t], z[3]));
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int jr = w - 1 - (x0 + c);
-            if (jr >= 1 && jr <= P) {
-              o[c] = fmaf(sk[P - jr], g0, o[c]);
-              if (SIG) z[c] = fmaf(sdk[P - jr], g0, fmaf(sk[P - jr], gd0, z[c]));
-            }
-          }
-        }
-      }
-      if (live && yo < h) {
-        if (STORE) *reinterpret_cast<float4*>(dst + mapoff + (long long)yo * w + x0) = make_float4(o[0], o[1], o[2], o[3]);
-        if (SIG)
-          acc_sigma = fmaf(xrow.x, z[0], fmaf(xrow.y, z[1], fmaf(xrow.z, z[2], fmaf(xrow.w, z[3], acc_sigma))));
+        const int j = x0 + c;
+        if (j >= 1 && j <= P) line[LPAD - j] = vv[c];
+        const int jr = w - 1 - j;
+        if (jr >= 1 && jr <= P) line[LPAD + w - 1 + jr] = vv[c];
       }
     }
-  }
-  if (SIG) {
-    acc_sigma = warp_sum(acc_sigma);
-    if ((threadIdx.x & 31) == 0) wred[threadIdx.x >> 5] = acc_sigma;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      float s = 0.f;
+    float seg[4 + 2 * P];
 #pragma unroll
-      for (int i = 0; i < THREADS / 32; ++i) s += wred[i];
-      partials[blockIdx.x] = s;
+    for (int i = 0; i < 4 + 2 * P; ++i) seg[i] = line[LPAD + x0 - P + i];
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+      for (int t = 0; t < KS; ++t) o[c] = fmaf(k[t], seg[c + t], o[c]);
     }
+    if (ADJ) {
+      const float dr = (yo == 0 || yo == h - 1) ? 0.5f : 1.f;   // D, rows
+      o[0] *= dr * d0; o[1] *= dr; o[2] *= dr; o[3] *= dr * d3;
+    }
+    if (live && yo < h)
+      *reinterpret_cast<float4*>(dst + mapoff + (long long)yo * w + x0) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -254,12 +174,20 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ aux, i
 // dk/dsigma): the vertical pass accumulates (v, v') per column from the window sample broadcast
 // against the tap pair (k[t], k'[t]); the shared line holds those pairs interleaved; the horizontal
 // pass forms (sum_t k[t] v, sum_t k[t] v') packed plus sum_t k'[t] v scalar.  The taps are symmetric,
-// so mirrored window samples are added first (P + 1 multiplies per output instead of 2P + 1).  Rows
-// at the top / bottom border differ from the symmetric stencil by at most P taps, applied as a
-// correction under a warp-uniform branch.  Same data path (register ring, double-buffered line,
-// one barrier per row), half the instructions of the scalar formulation.
+// so mirrored window samples are added first (P + 1 multiplies per output instead of 2P + 1).  The
+// adjoint borders are the E / D scalings derived above blur_fast_kernel (they apply to k and k'
+// alike).  Same data path (register ring, double-buffered line, one barrier per row), well under
+// half the instructions of the scalar formulation.
+// 160 registers / 3 CTAs per SM with the rolled RS-row unroll measured best (1.11 ms at 4096 maps of
+// 256^2; capped at 128 registers 1.29 ms, all rows unrolled 1.26 ms, both 1.18 ms)
+#ifndef FAVAE_ADJSIG_MINB
+#define FAVAE_ADJSIG_MINB 3
+#endif
+#ifndef FAVAE_ADJSIG_FULL
+#define FAVAE_ADJSIG_FULL 0
+#endif
 template <int KS, int TH>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, FAVAE_ADJSIG_MINB)
 blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux, int h, int w, long long items,
                    int strips, const float* __restrict__ sigma, float* __restrict__ dst,
                    float* __restrict__ partials) {
@@ -290,11 +218,13 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
   static_assert(RS % XQ == 0, "x prefetch ring must tile the unroll factor");
   const long long mapoff = map * (long long)h * w;
   auto load_row = [&](int r) -> float4 {
-    const int yi = y0 - P + r;
+    const int ry = reflect_idx(y0 - P + r, h);
     float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) in = ld4(base + (long long)reflect_idx(yi, h) * w + x0);
+    if (live) in = ld4(base + (long long)ry * w + x0);
     return in;
   };
+  const float e0 = tx == 0 ? 2.f : 1.f, e3 = tx == tpi - 1 ? 2.f : 1.f;     // E, columns
+  const float d0 = tx == 0 ? 0.5f : 1.f, d3 = tx == tpi - 1 ? 0.5f : 1.f;   // D, columns
   auto load_x = [&](int r) -> float4 {           // x row of the output produced at iteration r
     const int yo = y0 + r - (KS - 1);
     float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -306,7 +236,7 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
   for (int q = 0; q < RS; ++q) ring[q] = (q < Q) ? load_row(q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int q = 0; q < XQ; ++q) xq[q] = load_x(q);
-  constexpr int STEP = RS;                       // unrolling all NR rows was slower (code size)
+  constexpr int STEP = FAVAE_ADJSIG_FULL ? NR : RS;
 #pragma unroll 1
   for (int r0 = 0; r0 < NR; r0 += STEP) {
 #pragma unroll
@@ -317,6 +247,10 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
       if (r + Q < NR) ring[(u + Q) % RS] = load_row(r + Q);
       const float4 xrow = xq[u % XQ];
       if (r + XQ < NR) xq[u % XQ] = load_x(r + XQ);
+      {                                            // E, rows: doubled when the row enters the window
+        const int ry = reflect_idx(y0 - P + r, h);
+        if (ry == 0 || ry == h - 1) { float4& b = ring[u]; b.x *= 2.f; b.y *= 2.f; b.z *= 2.f; b.w *= 2.f; }
+      }
       if (r < KS - 1) continue;
       const int yo = y0 + r - (KS - 1);            // output row of this iteration
 #define FAVAE_WIN(t) ring[(u + RS - (KS - 1) + (t)) % RS]
@@ -336,25 +270,7 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
           acc[2] = pk_fma(pk_dup(s23.x), kd[t], acc[2]); acc[3] = pk_fma(pk_dup(s23.y), kd[t], acc[3]);
         }
       }
-      // border rows of the adjoint (see the derivation above blur_fast_kernel): the border output
-      // takes no mirrored taps; outputs 1..P next to a border take the border sample once more
-      const int jrow = h - 1 - yo;
-      if (live && (yo <= P || (jrow >= 0 && jrow <= P))) {
-        auto axpy = [&](const float4& g, float2 kk) {
-          acc[0] = pk_fma(pk_dup(g.x), kk, acc[0]); acc[1] = pk_fma(pk_dup(g.y), kk, acc[1]);
-          acc[2] = pk_fma(pk_dup(g.z), kk, acc[2]); acc[3] = pk_fma(pk_dup(g.w), kk, acc[3]);
-        };
-        if (yo == 0) {
-#pragma unroll
-          for (int t = 0; t < P; ++t) axpy(FAVAE_WIN(t), make_float2(-kd[t].x, -kd[t].y));
-        }
-        if (jrow == 0) {
-#pragma unroll
-          for (int t = 0; t < P; ++t) axpy(FAVAE_WIN(KS - 1 - t), make_float2(-kd[t].x, -kd[t].y));
-        }
-        if (yo >= 1 && yo <= P) axpy(ld4(base + x0), make_float2(sk[P - yo], sdk[P - yo]));
-        if (jrow >= 1 && jrow <= P) axpy(ld4(base + (long long)(h - 1) * w + x0), make_float2(sk[P - jrow], sdk[P - jrow]));
-      }
+      acc[0] = pk_mul(acc[0], pk_dup(e0)); acc[3] = pk_mul(acc[3], pk_dup(e3));
 #undef FAVAE_WIN
       // ---- horizontal pass through a shared line of (v, v') pairs
       float2* line = lines2 + (size_t)((r & 1) * groups + grp) * ll;
@@ -396,43 +312,10 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
         }
         o[c] = a2.x; z[c] = a2.y + za;
       }
-      if (tx == 0 || (tx == 1 && P > 3)) {
-        const float2 g0 = line[LPAD];
-        if (tx == 0) {
-          o[0] = 0.f; z[0] = 0.f;                        // column 0: only the taps inside the map
-#pragma unroll
-          for (int t = P; t < KS; ++t) {
-            o[0] = fmaf(k[t], seg[t].x, o[0]);
-            z[0] = fmaf(dk[t], seg[t].x, fmaf(k[t], seg[t].y, z[0]));
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {                    // columns 1..P: the border sample itself
-          const int j = x0 + c;
-          if (j >= 1 && j <= P) {
-            o[c] = fmaf(sk[P - j], g0.x, o[c]);
-            z[c] = fmaf(sdk[P - j], g0.x, fmaf(sk[P - j], g0.y, z[c]));
-          }
-        }
-      }
-      if (tx == tpi - 1 || (tx == tpi - 2 && P > 3)) {
-        const float2 g0 = line[LPAD + w - 1];
-        if (tx == tpi - 1) {
-          o[3] = 0.f; z[3] = 0.f;
-#pragma unroll
-          for (int t = 0; t <= P; ++t) {
-            o[3] = fmaf(k[t], seg[3 + t].x, o[3]);
-            z[3] = fmaf(dk[t], seg[3 + t].x, fmaf(k[t], seg[3 + t].y, z[3]));
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const int jr = w - 1 - (x0 + c);
-          if (jr >= 1 && jr <= P) {
-            o[c] = fmaf(sk[P - jr], g0.x, o[c]);
-            z[c] = fmaf(sdk[P - jr], g0.x, fmaf(sk[P - jr], g0.y, z[c]));
-          }
-        }
+      {
+        const float dr = (yo == 0 || yo == h - 1) ? 0.5f : 1.f;   // D, rows
+        o[0] *= dr * d0; o[1] *= dr; o[2] *= dr; o[3] *= dr * d3;
+        z[0] *= dr * d0; z[1] *= dr; z[2] *= dr; z[3] *= dr * d3;
       }
       if (live && yo < h) {
         *reinterpret_cast<float4*>(dst + mapoff + (long long)yo * w + x0) = make_float4(o[0], o[1], o[2], o[3]);
@@ -454,8 +337,8 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
 // MODE_SIGMA with the same packed arithmetic: d/dsigma <gy, H V x> = <gy, (H'V + HV') x> on the forward
 // data path (reflect halos only, no border corrections, nothing stored): x goes through the
 // (V x, V' x) / (H ., H' .) pair pipeline of blur_adjsig_kernel and each finished row is dotted
-// with the matching gy row.  Together with MODE_ADJ this replaces the fused adjoint + sigma kernel
-// when the two lean kernels are faster than the fused one.
+// with the matching gy row.  Together with MODE_ADJ it is the FAVAE_BLUR_SIGMA=split alternative to
+// the fused adjoint + sigma kernel (two lean kernels, 16 instead of 12 B/element).
 // Measured on B200 (4096 maps of 256^2, k = 9, together with the plain adjoint): rolled 15-row unroll
 // at 154 registers 1.03 ms; capped at 128 registers (4 CTAs / SM) 0.85 ms; all rows unrolled 0.95 ms;
 // both 0.69 ms.

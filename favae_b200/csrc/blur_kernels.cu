@@ -261,12 +261,10 @@ int favae_blur_backward(const float* gy, const float* x, int64_t maps, int h, in
   }
   if (gx && blurf::supported(h, w, ksize) && aligned16(gy) && aligned16(gx) && (!gsigma || aligned16(x))) {
     if (!gsigma) return blurf::launch<blurf::MODE_ADJ>(gy, nullptr, maps, h, w, ksize, sigma, gx, nullptr, s);
-    // Large maps: the plain adjoint plus the packed sigma-gradient kernel on the forward data path
-    // (16 B/element, but two lean kernels at 4-5 CTAs per SM: 1.24 ms against 1.43 ms for the fused
-    // 12 B/element kernel at 4096 maps of 256^2).  Small maps keep the single fused launch.
-    // FAVAE_BLUR_SIGMA=fused / split forces either.
-    static const int mode = [] { const char* e = getenv("FAVAE_BLUR_SIGMA"); return !e ? 0 : e[0] == 's' ? 1 : e[0] == 'f' ? 2 : 0; }();
-    const bool split = mode == 1 || (mode == 0 && h >= 64);
+    // One fused kernel (12 B/element: gy and x read once, gx written).  FAVAE_BLUR_SIGMA=split runs
+    // the plain adjoint and the forward-path sigma-gradient kernel instead (16 B/element).  Measured
+    // on B200 at 4096 maps of 256^2, k = 9: fused 1.11 ms, split 0.56 + 0.69 ms.
+    static const bool split = [] { const char* e = getenv("FAVAE_BLUR_SIGMA"); return e && e[0] == 's'; }();
     if (!split) {
       rc = blurf::launch<blurf::MODE_ADJ_SIG>(gy, x, maps, h, w, ksize, sigma, gx, partials, s);
     } else {

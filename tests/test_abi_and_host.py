@@ -100,3 +100,36 @@ def test_patch_reference_swaps_the_reference_modules():
         "print('ok', done)" % ROOT)
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and 'ok' in r.stdout, r.stderr[-2000:]
+
+
+def test_adjoint_as_forward_stencil_identity():
+    """The blur kernels run the adjoint of (reflect-pad, correlate) as a forward stencil on the array
+    with doubled border samples, halving the border outputs (favae_b200/csrc/blur_fast.cuh).  Check
+    the identity against autograd for every half-width P < w, including P = w - 1."""
+    import itertools
+    import torch
+    g0 = torch.Generator().manual_seed(0)
+
+    def fwd1d(x, k):
+        p = len(k) // 2
+        xp = torch.nn.functional.pad(x[None, None], (p, p), mode='reflect')[0, 0]
+        return torch.stack([(k * xp[i:i + len(k)]).sum() for i in range(len(x))])
+
+    def adjoint_by_forward_stencil(g, k):
+        w, p = len(g), len(k) // 2
+        e = g.clone(); e[0] *= 2; e[-1] *= 2
+        idx = [(-i if i < 0 else (2 * (w - 1) - i if i >= w else i)) for i in range(-p, w + p)]
+        ext = e[idx]
+        out = torch.stack([(k * ext[i:i + len(k)]).sum() for i in range(w)])
+        out[0] *= 0.5; out[-1] *= 0.5
+        return out
+
+    for w, p in itertools.product([4, 5, 8, 9, 16, 33], [1, 2, 4, 5, 7]):
+        if p >= w:
+            continue
+        k = torch.rand(2 * p + 1, dtype=torch.float64, generator=g0)
+        k = k + k.flip(0)                                   # symmetric taps, like the Gaussian and its sigma derivative
+        x = torch.randn(w, dtype=torch.float64, generator=g0, requires_grad=True)
+        g = torch.randn(w, dtype=torch.float64, generator=g0)
+        (fwd1d(x, k) * g).sum().backward()
+        assert (x.grad - adjoint_by_forward_stencil(g, k)).abs().max() < 1e-12, (w, p)
