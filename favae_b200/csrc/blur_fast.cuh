@@ -273,32 +273,42 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
       acc[0] = pk_mul(acc[0], pk_dup(e0)); acc[3] = pk_mul(acc[3], pk_dup(e3));
 #undef FAVAE_WIN
       // ---- horizontal pass through a shared line of (v, v') pairs
-      float2* line = lines2 + (size_t)((r & 1) * groups + grp) * ll;
-      *reinterpret_cast<float4*>(line + LPAD + x0) = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
-      *reinterpret_cast<float4*>(line + LPAD + x0 + 2) = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
-      if (tx == 0 || tx == tpi - 1 || (P > 3 && (tx == 1 || tx == tpi - 2))) {
-        // mirrored halo entries (reflect): index -j <- j, index w-1+j <- w-1-j
+      // Two planes of float4: plane A holds the pairs of columns 4q, 4q+1 of thread q,
+      // plane B those of columns 4q+2, 4q+3, LP halo slots on either side.  Every 128-bit access of a
+      // quarter warp then covers 128 contiguous bytes (the interleaved single line had a 32-byte thread
+      // stride: two-way bank conflicts on every access, 67 % shared-pipe utilisation).
+      constexpr int LP = 2, NB = (P + 3) / 4;
+      float4* planeA = reinterpret_cast<float4*>(lines2 + (size_t)((r & 1) * groups + grp) * ll);
+      float4* planeB = planeA + (tpi + 2 * LP);
+      planeA[LP + tx] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+      planeB[LP + tx] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+      if (tx <= P / 4 || tx >= tpi - 1 - P / 4) {   // owners of columns 1..P and w-1-P..w-2
+        auto put = [&](int col, float2 v) {        // pair of map column col (halo columns included)
+          const int q = (col + 4 * LP) / 4 - LP, c = col - 4 * q;
+          float2* pl = reinterpret_cast<float2*>(c < 2 ? planeA : planeB);
+          pl[2 * (LP + q) + (c & 1)] = v;
+        };
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 4; ++c) {              // reflect: column -j <- j, column w-1+j <- w-1-j
           const int j = x0 + c;
-          if (j >= 1 && j <= P) line[LPAD - j] = acc[c];
+          if (j >= 1 && j <= P) put(-j, acc[c]);
           const int jr = w - 1 - j;
-          if (jr >= 1 && jr <= P) line[LPAD + w - 1 + jr] = acc[c];
+          if (jr >= 1 && jr <= P) put(w - 1 + jr, acc[c]);
         }
       }
       __syncthreads();
-      float2 seg[4 + 2 * P];
-      if constexpr (P % 2 == 0) {                  // LPAD + x0 - P is even: 16-byte aligned pairs of pairs
-        const float4* l4 = reinterpret_cast<const float4*>(line + LPAD + x0 - P);
+      float2 cols[4 * (2 * NB + 1)];               // columns x0 - 4 NB .. x0 + 4 NB + 3; own from registers
 #pragma unroll
-        for (int i = 0; i < 2 + P; ++i) {
-          const float4 q = l4[i];
-          seg[2 * i] = make_float2(q.x, q.y); seg[2 * i + 1] = make_float2(q.z, q.w);
+      for (int q = -NB; q <= NB; ++q) {
+        float2* d = cols + 4 * (q + NB);
+        if (q == 0) { d[0] = acc[0]; d[1] = acc[1]; d[2] = acc[2]; d[3] = acc[3]; }
+        else {
+          const float4 a = planeA[LP + tx + q], b = planeB[LP + tx + q];
+          d[0] = make_float2(a.x, a.y); d[1] = make_float2(a.z, a.w);
+          d[2] = make_float2(b.x, b.y); d[3] = make_float2(b.z, b.w);
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4 + 2 * P; ++i) seg[i] = line[LPAD + x0 - P + i];
       }
+      const float2* seg = cols + (4 * NB - P);     // seg[i] = column x0 - P + i
       float o[4], z[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
