@@ -65,13 +65,14 @@ __device__ __forceinline__ void load_weights(const float* sigma_ptr, float* sk, 
 // which would receive every contribution twice, is halved (D).  (Checked against autograd for
 // every P < w, including P = w - 1, in tests/test_abi_and_host.py.)  The adjoint therefore runs the
 // forward data path with two scalings per border instead of per-row tap masks and corrections.
-// adjoint: rolled RS-row unroll at 128 registers (4 CTAs / SM) measured best (0.565 ms at 4096 maps
-// of 256^2; all rows unrolled 0.71 ms, 146 registers 0.63 ms, 96 registers with spills 0.67 ms)
+// adjoint: rolled RS-row unroll, 3 rows in flight, 96 registers (5 CTAs / SM), 64-row strips on large
+// maps: 0.47 ms at 4096 maps of 256^2.  (6 rows in flight at 128 registers / 4 CTAs: 0.57 ms; all rows
+// unrolled 0.71 ms; 6 rows capped at 96 registers spills: 0.67 ms.)
 #ifndef FAVAE_ADJ_FULL
 #define FAVAE_ADJ_FULL 0
 #endif
 #ifndef FAVAE_ADJ_MINB
-#define FAVAE_ADJ_MINB 4
+#define FAVAE_ADJ_MINB 5
 #endif
 template <int KS, int TH, int MODE>
 __global__ void __launch_bounds__(THREADS, MODE == MODE_ADJ ? FAVAE_ADJ_MINB : 5)
@@ -101,9 +102,13 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ /*aux*
   const float d0 = (ADJ && tx == 0) ? 0.5f : 1.f, d3 = (ADJ && tx == tpi - 1) ? 0.5f : 1.f; // D, columns
 
   // Register ring of RS = KS + Q rows: the KS-row window of the vertical pass plus Q rows in flight
-  // from HBM (explicit prefetch: ~6 rows per thread are needed to cover the HBM latency at this
-  // occupancy).  All NR rows are unrolled so every ring index is a constant.
-  constexpr int Q = 6 + ((3 - (KS + 6) % 3) % 3), RS = KS + Q, NR = TH + KS - 1;
+  // from HBM (explicit prefetch: 6 rows per thread for the forward kernel, whose NR rows are all
+  // unrolled; 3 for the adjoint, which trades prefetch depth for a fifth CTA per SM and unrolls RS
+  // rows inside a rolled loop).  Every ring index is a constant.
+#ifndef FAVAE_ADJ_Q
+#define FAVAE_ADJ_Q 3
+#endif
+  constexpr int Q = ADJ ? FAVAE_ADJ_Q : 6 + ((3 - (KS + 6) % 3) % 3), RS = KS + Q, NR = TH + KS - 1;
   const long long mapoff = map * (long long)h * w;
   auto load_row = [&](int r) -> float4 {
     const int ry = reflect_idx(y0 - P + r, h);
@@ -178,10 +183,12 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ /*aux*
 // adjoint borders are the E / D scalings derived above blur_fast_kernel (they apply to k and k'
 // alike).  Same data path (register ring, double-buffered line, one barrier per row), well under
 // half the instructions of the scalar formulation.
-// 160 registers / 3 CTAs per SM with the rolled RS-row unroll measured best (1.11 ms at 4096 maps of
-// 256^2; capped at 128 registers 1.29 ms, all rows unrolled 1.26 ms, both 1.18 ms)
+// Occupancy is what this kernel needs: with 3 rows of gy in flight (instead of 6) and the x row
+// requested in the iteration that uses it, the kernel fits 126 registers without spills, i.e. 4 CTAs
+// (16 warps) per SM: 0.88 ms at 4096 maps of 256^2 against 1.11 ms at 160 registers / 3 CTAs.
+// (Capping the 6-row version at 128 registers spilled: 1.29 ms; all rows unrolled 1.26 ms.)
 #ifndef FAVAE_ADJSIG_MINB
-#define FAVAE_ADJSIG_MINB 3
+#define FAVAE_ADJSIG_MINB 4
 #endif
 #ifndef FAVAE_ADJSIG_FULL
 #define FAVAE_ADJSIG_FULL 0
@@ -214,7 +221,14 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
   const float* base = src + map * (long long)h * w;
   float acc_sigma = 0.f;
 
-  constexpr int Q = 6 + ((3 - (KS + 6) % 3) % 3), RS = KS + Q, XQ = 3, NR = TH + KS - 1;
+#ifndef FAVAE_ADJSIG_Q
+#define FAVAE_ADJSIG_Q 3
+#endif
+#ifndef FAVAE_ADJSIG_XQ
+#define FAVAE_ADJSIG_XQ 1
+#endif
+  constexpr int XQ = FAVAE_ADJSIG_XQ;
+  constexpr int Q = FAVAE_ADJSIG_Q + ((XQ - (KS + FAVAE_ADJSIG_Q) % XQ) % XQ), RS = KS + Q, NR = TH + KS - 1;
   static_assert(RS % XQ == 0, "x prefetch ring must tile the unroll factor");
   const long long mapoff = map * (long long)h * w;
   auto load_row = [&](int r) -> float4 {
@@ -498,9 +512,23 @@ inline bool supported(int h, int w, int ks) {
   // w >= 8 keeps the two border-owning threads distinct; halo slots need ks/2 <= LPAD
   return pow2 && w >= 8 && kok && ks / 2 < h && ks / 2 < w && ks / 2 <= LPAD;
 }
-inline int strip_rows(int h) { return h <= 16 ? 16 : 32; }
-inline long long num_blocks(long long maps, int h, int w) {
-  const int th = strip_rows(h), strips = (h + th - 1) / th, groups = THREADS / (w / 4);
+// Strip height.  The kernels with a fully unrolled row loop use 32 (16 for small maps); the fused
+// adjoint + sigma kernel (rolled loop, so the height is free) takes taller strips on large maps: a
+// strip re-reads KS - 1 halo rows, 25 % of its loads at 32 rows, 12.5 % at 64 (1.10 -> 0.79 ms together
+// with the occupancy change above).
+#ifndef FAVAE_ADJSIG_TH
+#define FAVAE_ADJSIG_TH 64
+#endif
+#ifndef FAVAE_ADJ_TH
+#define FAVAE_ADJ_TH 64
+#endif
+inline int strip_rows(int h, int mode = MODE_FWD) {
+  if (mode == MODE_ADJ_SIG && h >= 2 * FAVAE_ADJSIG_TH) return FAVAE_ADJSIG_TH;
+  if (mode == MODE_ADJ && h >= 2 * FAVAE_ADJ_TH) return FAVAE_ADJ_TH;
+  return h <= 16 ? 16 : 32;
+}
+inline long long num_blocks(long long maps, int h, int w, int mode = MODE_FWD) {
+  const int th = strip_rows(h, mode), strips = (h + th - 1) / th, groups = THREADS / (w / 4);
   return (maps * strips + groups - 1) / groups;
 }
 
@@ -526,8 +554,12 @@ static int launch(const float* src, const float* aux, long long maps, int h, int
                   float* dst, float* partials, cudaStream_t s) {
 #define FAVAE_BLUR_CASE(KS)                                                                         \
   case KS:                                                                                          \
-    return strip_rows(h) == 16 ? launch_one<KS, 16, MODE>(src, aux, maps, h, w, sigma, dst, partials, s) \
-                               : launch_one<KS, 32, MODE>(src, aux, maps, h, w, sigma, dst, partials, s);
+    if (MODE == MODE_ADJ_SIG && strip_rows(h, MODE) == FAVAE_ADJSIG_TH)                             \
+      return launch_one<KS, (MODE == MODE_ADJ_SIG ? FAVAE_ADJSIG_TH : 32), MODE>(src, aux, maps, h, w, sigma, dst, partials, s); \
+    if (MODE == MODE_ADJ && strip_rows(h, MODE) == FAVAE_ADJ_TH)                                    \
+      return launch_one<KS, (MODE == MODE_ADJ ? FAVAE_ADJ_TH : 32), MODE>(src, aux, maps, h, w, sigma, dst, partials, s); \
+    return strip_rows(h, MODE) == 16 ? launch_one<KS, 16, MODE>(src, aux, maps, h, w, sigma, dst, partials, s) \
+                                     : launch_one<KS, 32, MODE>(src, aux, maps, h, w, sigma, dst, partials, s);
   switch (ks) {
     FAVAE_BLUR_CASE(3)
     FAVAE_BLUR_CASE(5)

@@ -273,7 +273,8 @@ int favae_blur_backward(const float* gy, const float* x, int64_t maps, int h, in
       rc = blurf::launch<blurf::MODE_SIGMA>(x, gy, maps, h, w, ksize, sigma, nullptr, partials, s);
     }
     if (rc) return rc;
-    return favae_sum_scaled(partials, blurf::num_blocks(maps, h, w), 1.0, gsigma, stream);
+    return favae_sum_scaled(partials, blurf::num_blocks(maps, h, w, split ? blurf::MODE_SIGMA : blurf::MODE_ADJ_SIG), 1.0,
+                            gsigma, stream);
   }
   const unsigned blocks = (unsigned)blur_blocks(maps, h, w);
   if (gx) {
