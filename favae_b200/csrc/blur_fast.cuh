@@ -75,7 +75,19 @@ __device__ __forceinline__ void load_weights(const float* sigma_ptr, float* sk, 
 #define FAVAE_ADJ_MINB 5
 #endif
 template <int KS, int TH, int MODE>
-__global__ void __launch_bounds__(THREADS, MODE == MODE_ADJ ? FAVAE_ADJ_MINB : 5)
+#ifndef FAVAE_FWD_FULL
+#define FAVAE_FWD_FULL 1
+#endif
+#ifndef FAVAE_FWD_MINB
+#define FAVAE_FWD_MINB 5
+#endif
+#ifndef FAVAE_FWD_Q
+#define FAVAE_FWD_Q 6
+#endif
+#ifndef FAVAE_FWD_TH
+#define FAVAE_FWD_TH 32
+#endif
+__global__ void __launch_bounds__(THREADS, MODE == MODE_ADJ ? FAVAE_ADJ_MINB : FAVAE_FWD_MINB)
 blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ /*aux*/, int h, int w, long long items,
                  int strips, const float* __restrict__ sigma, float* __restrict__ dst,
                  float* __restrict__ /*partials*/) {
@@ -108,7 +120,7 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ /*aux*
 #ifndef FAVAE_ADJ_Q
 #define FAVAE_ADJ_Q 3
 #endif
-  constexpr int Q = ADJ ? FAVAE_ADJ_Q : 6 + ((3 - (KS + 6) % 3) % 3), RS = KS + Q, NR = TH + KS - 1;
+  constexpr int Q = ADJ ? FAVAE_ADJ_Q : FAVAE_FWD_Q, RS = KS + Q, NR = TH + KS - 1;
   const long long mapoff = map * (long long)h * w;
   auto load_row = [&](int r) -> float4 {
     const int ry = reflect_idx(y0 - P + r, h);
@@ -119,7 +131,7 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ /*aux*
   float4 ring[RS];
 #pragma unroll
   for (int q = 0; q < RS; ++q) ring[q] = (q < Q) ? load_row(q) : make_float4(0.f, 0.f, 0.f, 0.f);
-  constexpr int STEP = (ADJ && !FAVAE_ADJ_FULL) ? RS : NR;
+  constexpr int STEP = ((ADJ && !FAVAE_ADJ_FULL) || (!ADJ && !FAVAE_FWD_FULL)) ? RS : NR;
 #pragma unroll 1
   for (int r0 = 0; r0 < NR; r0 += STEP)
 #pragma unroll
@@ -525,6 +537,7 @@ inline bool supported(int h, int w, int ks) {
 inline int strip_rows(int h, int mode = MODE_FWD) {
   if (mode == MODE_ADJ_SIG && h >= 2 * FAVAE_ADJSIG_TH) return FAVAE_ADJSIG_TH;
   if (mode == MODE_ADJ && h >= 2 * FAVAE_ADJ_TH) return FAVAE_ADJ_TH;
+  if (mode == MODE_FWD && FAVAE_FWD_TH > 32 && h >= 2 * FAVAE_FWD_TH) return FAVAE_FWD_TH;
   return h <= 16 ? 16 : 32;
 }
 inline long long num_blocks(long long maps, int h, int w, int mode = MODE_FWD) {
@@ -556,6 +569,8 @@ static int launch(const float* src, const float* aux, long long maps, int h, int
   case KS:                                                                                          \
     if (MODE == MODE_ADJ_SIG && strip_rows(h, MODE) == FAVAE_ADJSIG_TH)                             \
       return launch_one<KS, (MODE == MODE_ADJ_SIG ? FAVAE_ADJSIG_TH : 32), MODE>(src, aux, maps, h, w, sigma, dst, partials, s); \
+    if (MODE == MODE_FWD && FAVAE_FWD_TH > 32 && strip_rows(h, MODE) == FAVAE_FWD_TH)               \
+      return launch_one<KS, (MODE == MODE_FWD ? FAVAE_FWD_TH : 32), MODE>(src, aux, maps, h, w, sigma, dst, partials, s); \
     if (MODE == MODE_ADJ && strip_rows(h, MODE) == FAVAE_ADJ_TH)                                    \
       return launch_one<KS, (MODE == MODE_ADJ ? FAVAE_ADJ_TH : 32), MODE>(src, aux, maps, h, w, sigma, dst, partials, s); \
     return strip_rows(h, MODE) == 16 ? launch_one<KS, 16, MODE>(src, aux, maps, h, w, sigma, dst, partials, s) \
