@@ -443,7 +443,9 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
   env.mark(7);
 
   // ---------------- P6: inverse row FFTs, S -> gradient rows ----------------
-  for (int pass = 0; pass < PASSES; ++pass) {
+  // The gather of pass p + 1 (half of it distributed-shared-memory loads from the peer) is issued
+  // before the gradient stores of pass p, when the payload registers are free again.
+  auto gather = [&](int pass) {
     env.for_threads([&](int cta, int tid) {
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
       const int g = tid / TG, t = tid % TG, item = pass * NG + g;
@@ -452,6 +454,13 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       const int at = IS * rp + (Cfg::S_ENTRY_MAJOR ? 0 : m * (GPC * 2 * Cfg::COLSTRIDE));
 #pragma unroll
       for (int e = 0; e < R1; ++e) r.v[e] = env.s_get(cta, tab[idx_out<Cfg>(t, e)], at);
+    });
+  };
+  gather(0);
+  for (int pass = 0; pass < PASSES; ++pass) {
+    env.for_threads([&](int cta, int tid) {
+      ThreadRegs<Cfg>& r = env.regs(cta, tid);
+      const int g = tid / TG, t = tid % TG;
       env.mark(8);
       inv_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
       // last read of S: release it for the next map.  inv_stage1 has consumed every loaded value, so
@@ -478,6 +487,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
     });
     env.sync_warp();
     env.mark(9);
+    if (pass + 1 < PASSES) gather(pass + 1);
     // the next batch's first rows start their trip from HBM / L2 under this pass's gradient stores
     if (Cfg::PIPELINE_LOADS && pass == PASSES - 1 && next_batch >= 0) ffl_issue_loads<Cfg>(env, p, next_batch, 0);
     env.for_threads([&](int cta, int tid) {

@@ -44,6 +44,26 @@ def test_ffl_option_flags(kw):
     _run((2, 3, 32, 32), seed=3, loss_weight=0.5, **kw)
 
 
+def test_ffl_negative_weight_takes_the_general_kernel():
+    """alpha = 1 normally runs the lean statistics instantiation, which folds the (non-negative)
+    gradient scale into the clamp; a negative loss weight must fall back to the general one."""
+    _run((2, 3, 64, 64), seed=5, loss_weight=-0.3, alpha=1.0)
+    _run((1, 2, 256, 256), seed=6, loss_weight=-0.3, alpha=1.0)
+
+
+def test_ffl_lean_and_general_instantiations_agree():
+    """Same inputs through the alpha = 1 fast path and through the general path (forced by a
+    negative upstream scale on a negated weight): identical loss, gradients equal to rounding."""
+    from favae_b200 import FocalFrequencyLoss
+    g = torch.Generator().manual_seed(11)
+    p = torch.randn(2, 4, 256, 256, generator=g).cuda(); t = torch.randn(2, 4, 256, 256, generator=g).cuda()
+    p1 = p.clone().requires_grad_(True); p2 = p.clone().requires_grad_(True)
+    l1 = FocalFrequencyLoss(loss_weight=0.5)(p1, t); l1.backward()
+    l2 = FocalFrequencyLoss(loss_weight=-0.5)(p2, t); (-l2).backward()
+    assert float(l1) == pytest.approx(-float(l2), rel=1e-6)
+    assert (p1.grad - p2.grad).abs().max() <= 1e-5 * p1.grad.abs().max()
+
+
 def test_ffl_baseline_feature_shapes():
     """The four feature levels of the f=16 model at batch 1."""
     for shape in [(1, 128, 256, 256), (1, 512, 16, 16), (1, 256, 16, 16)]:
