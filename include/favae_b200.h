@@ -115,7 +115,10 @@ int favae_vq_gather_rows(const float* embed, const int64_t* idx, int64_t n, int6
  * grad_pred / grad_target (nullable) receive +/- grad_scale * N^2 * Re ifft2(w . F) -- pass
  * grad_scale = 2 * loss_weight / numel.
  * map_max (nullable) receives max_{u,v} f(|F|) per map; fmax_override (nullable, one device
- * scalar) replaces the per-map maximum in the weight (batch_matrix=True). */
+ * scalar) replaces the per-map maximum in the weight (batch_matrix=True).
+ * alpha == 1 without log weighting and grad_scale >= 0 (every call the reference makes) runs a
+ * leaner instantiation of the same kernel; results agree with the general one to rounding.
+ * Diagnostics only: FAVAE_FFL256=c4 selects the 4-CTA-cluster variant for 256 x 256 maps. */
 int favae_ffl_supported(int h, int w);
 int favae_ffl_forward(const float* pred, const float* target, int64_t maps, int h, int w,
                       float alpha, int log_matrix, float grad_scale, float* map_loss,
@@ -137,7 +140,8 @@ int favae_scale_inplace(float* a, float* b, int64_t n, const float* s, void* str
 int favae_blur_forward(const float* x, int64_t maps, int h, int w, int ksize, const float* sigma,
                        float* y, void* stream);
 /* gx = adjoint blur of gy;  gsigma[0] = d/dsigma <gy, blur(x)> (nullable; partials =
- * favae_blur_partials(maps,h,w) floats of scratch). */
+ * favae_blur_partials(maps,h,w) floats of scratch).  Diagnostics only: the environment variable
+ * FAVAE_BLUR_SIGMA=split computes the two results with two kernels instead of the fused one. */
 int64_t favae_blur_partials(int64_t maps, int h, int w);
 int favae_blur_backward(const float* gy, const float* x, int64_t maps, int h, int w, int ksize,
                         const float* sigma, float* gx, float* gsigma, float* partials,
