@@ -100,22 +100,25 @@ template <int DIR> FAVAE_HD float2 crot(float2 a) {
   return DIR < 0 ? make_float2(a.y, -a.x) : make_float2(-a.y, a.x);
 }
 
-// twiddle e^{DIR * 2*pi*i * j/16}, j = 0..7, as compile-time constants:
+// twiddle e^{DIR * 2*pi*i * j/32}, j = 0..15, as compile-time constants:
 // a * (c + i s) = a (.) (c, c) + swap(a) (.) (-s, s), two packed operations
-template <int J, int DIR> FAVAE_HD float2 ctw16(float2 a) {
-  constexpr float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, R2 = 0.70710678118654752f;
+template <int J, int DIR> FAVAE_HD float2 ctw32(float2 a) {
+  // cos(pi j / 16), j = 0..8
+  constexpr float C[9] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                          0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f,
+                          0.19509032201612825f, 0.0f};
   if constexpr (J == 0) return a;
-  else if constexpr (J == 4) return crot<DIR>(a);
+  else if constexpr (J == 8) return crot<DIR>(a);
   else {
-    constexpr float c = (J == 1) ? C1 : (J == 2) ? R2 : (J == 3) ? S1 : (J == 5) ? -S1 : (J == 6) ? -R2 : -C1;
-    constexpr float s0 = (J == 1) ? S1 : (J == 2) ? R2 : (J == 3) ? C1 : (J == 5) ? C1 : (J == 6) ? R2 : S1;
+    constexpr float c = (J < 8) ? C[J] : -C[16 - J];
+    constexpr float s0 = (J < 8) ? C[8 - J] : C[J - 8];
     constexpr float s = DIR < 0 ? -s0 : s0;
     return pk_fma(pk_swap(a), make_float2(-s, s), pk_mul(a, make_float2(c, c)));
   }
 }
 
 // ----------------------------------------------------------------------------------
-// in-register FFT of R in {1,2,4,8,16} values, natural order in and out
+// in-register FFT of R in {1,2,4,8,16,32} values, natural order in and out
 // ----------------------------------------------------------------------------------
 template <int R, int DIR> struct RegFFT;
 
@@ -131,7 +134,7 @@ template <int DIR> struct RegFFT<2, DIR> {
 
 template <int R, int DIR, int K> struct Combine {
   static FAVAE_HD void run(float2 (&v)[R], const float2 (&e)[R / 2], const float2 (&o)[R / 2]) {
-    float2 t = ctw16<K * (16 / R), DIR>(o[K]);
+    float2 t = ctw32<K * (32 / R), DIR>(o[K]);
     v[K] = cadd(e[K], t);
     v[K + R / 2] = csub(e[K], t);
     if constexpr (K + 1 < R / 2) Combine<R, DIR, K + 1>::run(v, e, o);
@@ -159,6 +162,7 @@ template <> struct FftGeom<32>  { static constexpr int R1 = 8,  R2 = 4; };
 template <> struct FftGeom<64>  { static constexpr int R1 = 8,  R2 = 8; };
 template <> struct FftGeom<128> { static constexpr int R1 = 16, R2 = 8; };
 template <> struct FftGeom<256> { static constexpr int R1 = 16, R2 = 16; };
+template <> struct FftGeom<512> { static constexpr int R1 = 32, R2 = 16; };
 
 // N: map side; C: CTAs per cluster sharing one map; MPC: maps per CTA (C==1 only)
 template <int N_, int C_, int MPC_, int THREADS_> struct FflCfg {

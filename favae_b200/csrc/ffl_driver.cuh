@@ -158,7 +158,8 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
   env.mark(2);
   // pull the next batch's rows of this CTA into L2 while this one is transformed (one bulk
   // prefetch per contiguous run of rows; a hint only)
-  if (next_batch >= 0 && next_batch * MPC < p.maps) {
+  auto prefetch_next = [&]() {
+    if (!(next_batch >= 0 && next_batch * MPC < p.maps)) return;
     env.for_threads([&](int cta, int tid) {
       if (tid == 0) {
         const long long nmaps = (p.maps - next_batch * MPC < MPC) ? p.maps - next_batch * MPC : MPC;
@@ -174,7 +175,10 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
         }
       }
     });
-  }
+  };
+#ifndef FAVAE_FFL_PF_LATE
+  prefetch_next();
+#endif
 
   // ---------------- P2: column FFTs + spectrum statistics ----------------
   for (int pass = 0; pass < PASSES; ++pass) {
@@ -377,6 +381,9 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
   env.sync_cta();
 
   env.mark(5);
+#ifdef FAVAE_FFL_PF_LATE
+  prefetch_next();
+#endif
   // ---------------- P5: weight + inverse column FFTs, re-pack into Z' ----------------
   for (int pass = 0; pass < PASSES; ++pass) {
     env.for_threads([&](int cta, int tid) {

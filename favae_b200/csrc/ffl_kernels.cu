@@ -1,6 +1,6 @@
 // CUDA instantiation of the fused spectrum-loss phases (ffl_driver.cuh) for sm_100a.
-// One CTA (N <= 128) or one 2-CTA cluster exchanging columns through distributed shared
-// memory (N = 256) owns a map from the first load to the gradient store: pred and target
+// One CTA (N <= 128) or one cluster exchanging columns through distributed shared memory
+// (N = 256: 2 CTAs, N = 512: 8 CTAs) owns a map from the first load to the gradient store: pred and target
 // are read once, both gradients written once, nothing else touches HBM.
 #include <cooperative_groups.h>
 #include <stdlib.h>
@@ -196,7 +196,7 @@ template <class Cfg> static int launch_ffl(const FflParams& p, cudaStream_t stre
 extern "C" {
 
 int favae_ffl_supported(int h, int w) {
-  return (h == w) && (h == 8 || h == 16 || h == 32 || h == 64 || h == 128 || h == 256);
+  return (h == w) && (h == 8 || h == 16 || h == 32 || h == 64 || h == 128 || h == 256 || h == 512);
 }
 
 int favae_ffl_forward(const float* pred, const float* target, int64_t maps, int h, int w,
@@ -205,7 +205,7 @@ int favae_ffl_forward(const float* pred, const float* target, int64_t maps, int 
                       const float* fmax_override, void* stream) {
   using namespace favae;
   FAVAE_REQUIRE(pred && target && map_loss, "ffl_forward: null pointer");
-  FAVAE_REQUIRE(favae_ffl_supported(h, w), "ffl_forward: maps must be square, side a power of two in [8,256]");
+  FAVAE_REQUIRE(favae_ffl_supported(h, w), "ffl_forward: maps must be square, side a power of two in [8,512]");
   FAVAE_REQUIRE(maps >= 0, "ffl_forward: negative map count");
   FAVAE_REQUIRE((((uintptr_t)pred | (uintptr_t)target | (uintptr_t)grad_pred | (uintptr_t)grad_target) & 15) == 0,
                 "ffl_forward: tensors must be 16-byte aligned");
@@ -222,6 +222,7 @@ int favae_ffl_forward(const float* pred, const float* target, int64_t maps, int 
     case 32: return launch_ffl<FflCfg32>(p, s);
     case 64: return launch_ffl<FflCfg64>(p, s);
     case 128: return launch_ffl<FflCfg128>(p, s);
+    case 512: return launch_ffl<FflCfg512>(p, s);   // 8-CTA cluster: 18 maps in flight on 144 SMs
     default: {
       // default: 2-CTA cluster, one map per SM pair.  FAVAE_FFL256=c4 selects the 4-CTA-cluster
       // variant (two maps in flight per SM), measured 14 % slower in round 1 (profiles/)

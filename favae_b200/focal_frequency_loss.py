@@ -138,7 +138,7 @@ class FocalFrequencyLoss(nn.Module):
         h, w = p.shape[-2:]
         if not _lib.load().favae_ffl_supported(h, w):
             raise NotImplementedError(f'favae_b200: spectrum loss needs square power-of-two maps with side '
-                                      f'in [8, 256], got {h}x{w}')
+                                      f'in [8, 512], got {h}x{w}')
         p, t = p.contiguous(), t.contiguous()
         if p.data_ptr() % 16:            # float4 access in the kernel
             p = p.clone()

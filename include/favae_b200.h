@@ -109,7 +109,7 @@ int favae_vq_gather_rows(const float* embed, const int64_t* idx, int64_t n, int6
 /* ------------------------------------------------------------------ spectrum losses */
 
 /* Fused focal-frequency / spectrum loss over `maps` independent h x w real maps (h == w, a
- * power of two in [8, 256]): replaces FocalFrequencyLoss.tensor2freq + loss_formulation
+ * power of two in [8, 512]): replaces FocalFrequencyLoss.tensor2freq + loss_formulation
  * (pip focal-frequency-loss==0.3.0; call sites losses/vqgan_losses.py:14,25-26,45-46) and
  * their autograd backward.  map_loss[m] = sum_{u,v} w * |F(pred - target)|^2 (ortho FFT);
  * grad_pred / grad_target (nullable) receive +/- grad_scale * N^2 * Re ifft2(w . F) -- pass

@@ -90,6 +90,31 @@ def main():
             ms = timed(lambda: _lib.call('favae_ffl_forward', xs.data_ptr(), gs_.data_ptr(), maps, 16, 16, 1.0, 0,
                                          1e-3, ml.data_ptr(), gp2.data_ptr(), gt2.data_ptr(), None, None, st()), it)
             print(f'ffl16 fwd+grad maps={maps:6d} {ms * 1e3:8.1f} us')
+    if want('f4'):
+        # the f = 4 model (BASELINE configs[3]): 64 x 64 feature maps, gaussian_kernel 3; level 0 is
+        # (B, 512, 64, 64) per side
+        maps = B * 512
+        E4 = maps * 64 * 64
+        xs = torch.randn(maps, 64, 64, device=dev); gs_ = torch.randn(maps, 64, 64, device=dev)
+        ys = torch.empty_like(xs); sg = torch.tensor(3.0, device=dev); g1 = torch.empty(1, device=dev)
+        parts = torch.empty(int(_lib.load().favae_blur_partials(maps, 64, 64)), device=dev)
+        ml = torch.empty(maps, device=dev); gp2 = torch.empty_like(xs); gt2 = torch.empty_like(xs)
+        for ks in (3, 9):
+            ms = timed(lambda: _lib.call('favae_blur_forward', xs.data_ptr(), maps, 64, 64, ks, sg.data_ptr(),
+                                         ys.data_ptr(), st()), it)
+            print(f'blur64 fwd k{ks}        {ms:8.3f} ms  {8 * E4 / ms / 1e6:8.1f} GB/s (8 B/elem)')
+            ms = timed(lambda: _lib.call('favae_blur_backward', gs_.data_ptr(), xs.data_ptr(), maps, 64, 64, ks,
+                                         sg.data_ptr(), ys.data_ptr(), g1.data_ptr(), parts.data_ptr(), st()), it)
+            print(f'blur64 bwd+sigma k{ks}  {ms:8.3f} ms  {12 * E4 / ms / 1e6:8.1f} GB/s (12 B/elem)')
+        ms = timed(lambda: _lib.call('favae_ffl_forward', xs.data_ptr(), gs_.data_ptr(), maps, 64, 64, 1.0, 0,
+                                     1e-3, ml.data_ptr(), gp2.data_ptr(), gt2.data_ptr(), None, None, st()), it)
+        print(f'ffl_64 fwd+grad       {ms:8.3f} ms  {16 * E4 / ms / 1e6:8.1f} GB/s algorithmic (16 B/elem)')
+        for n, side in ((B * 256, 128), (B * 1024, 32), (B * 32, 512)):
+            a = torch.randn(n, side, side, device=dev); b_ = torch.randn(n, side, side, device=dev)
+            ga = torch.empty_like(a); gb = torch.empty_like(a); mls = torch.empty(n, device=dev)
+            ms = timed(lambda: _lib.call('favae_ffl_forward', a.data_ptr(), b_.data_ptr(), n, side, side, 1.0, 0,
+                                         1e-3, mls.data_ptr(), ga.data_ptr(), gb.data_ptr(), None, None, st()), it)
+            print(f'ffl_{side} fwd+grad      {ms:8.3f} ms  {16 * a.numel() / ms / 1e6:8.1f} GB/s algorithmic (16 B/elem)')
     if want('vq'):
         K, D = 16384, 256
         for n in ([args.n_lat] if args.n_lat else [B * 256, 8192, 65536, 262144]):

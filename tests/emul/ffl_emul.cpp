@@ -78,6 +78,7 @@ extern "C" int ffl_emul(int n, const float* pred, const float* target, long long
     case 128: run<FflCfg128>(p); break;
     case 256: run<FflCfg256>(p); break;
     case 2564: run<FflCfg256c4>(p); break;
+    case 512: run<FflCfg512>(p); break;
     default: return -1;
   }
   return 0;

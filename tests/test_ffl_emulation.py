@@ -30,7 +30,7 @@ def emul():
 
 @pytest.mark.parametrize('n,maps,alpha,logm', [
     (8, 5, 1.0, 0), (8, 70, 1.0, 0), (16, 3, 1.0, 0), (16, 33, 1.0, 0), (32, 9, 1.0, 0),
-    (64, 2, 1.0, 0), (128, 1, 1.0, 0), (256, 1, 1.0, 0), (2564, 1, 1.0, 0),
+    (64, 2, 1.0, 0), (128, 1, 1.0, 0), (256, 1, 1.0, 0), (2564, 1, 1.0, 0), (512, 1, 1.0, 0),
     (16, 4, 2.0, 0), (32, 4, 0.5, 0), (16, 4, 1.0, 1), (64, 1, 1.5, 1)])
 def test_emulated_kernel_matches_oracle(emul, n, maps, alpha, logm):
     cfg, n = n, (256 if n == 2564 else n)       # 2564: the 4-CTA-cluster configuration of N = 256

@@ -32,7 +32,8 @@ def _run(shape, seed=0, **kw):
 
 
 @pytest.mark.parametrize('shape', [(2, 3, 8, 8), (3, 5, 16, 16), (2, 7, 32, 32), (2, 3, 64, 64),
-                                   (1, 3, 128, 128), (2, 3, 256, 256), (1, 37, 16, 16), (1, 130, 8, 8)])
+                                   (1, 3, 128, 128), (2, 3, 256, 256), (1, 37, 16, 16), (1, 130, 8, 8),
+                                   (1, 2, 512, 512), (5, 4, 512, 512)])
 def test_ffl_matches_oracle(shape):
     _run(shape, loss_weight=0.01, alpha=1.0)
 
