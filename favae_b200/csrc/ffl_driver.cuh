@@ -176,9 +176,15 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       }
     });
   };
-#ifndef FAVAE_FFL_PF_LATE
-  prefetch_next();
+  // Where the hint is issued matters: right here (a whole map time ahead of its use) 8 % of the
+  // prefetched lines are evicted again by the gradient stores streaming through L2 and the kernel
+  // is 5 % slower than with the hint at the start of P5 (measured, 4096 maps of 256^2).  Loss-only
+  // calls end after P3, so they prefetch here.
+#ifndef FAVAE_FFL_PF_POINT
+#define FAVAE_FFL_PF_POINT 5
 #endif
+  const bool want_grad = p.grad_pred != nullptr || p.grad_target != nullptr;
+  if (FAVAE_FFL_PF_POINT == 2 || !want_grad) prefetch_next();
 
   // ---------------- P2: column FFTs + spectrum statistics ----------------
   for (int pass = 0; pass < PASSES; ++pass) {
@@ -381,9 +387,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
   env.sync_cta();
 
   env.mark(5);
-#ifdef FAVAE_FFL_PF_LATE
-  prefetch_next();
-#endif
+  if (FAVAE_FFL_PF_POINT == 5) prefetch_next();
   // ---------------- P5: weight + inverse column FFTs, re-pack into Z' ----------------
   for (int pass = 0; pass < PASSES; ++pass) {
     env.for_threads([&](int cta, int tid) {
@@ -448,6 +452,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
   env.mark(6);
   env.sync_cluster();
   env.mark(7);
+  if (FAVAE_FFL_PF_POINT == 6) prefetch_next();
 
   // ---------------- P6: inverse row FFTs, S -> gradient rows ----------------
   // The gather of pass p + 1 (half of it distributed-shared-memory loads from the peer) is issued
