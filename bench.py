@@ -183,14 +183,45 @@ def time_cpu(batch, steps, warmup):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML is polled from a thread
+    every 10 ms (no process start-up latency: a 50-step run lasts ~0.2 s); `nvidia-smi -lms` is the
+    fallback when the NVML binding is missing."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
          'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    BITS = {'sw_power_cap': 0x4, 'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40}
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.sm, self.mx, self.reasons, self.stop_flag, self.thread = None, [], None, set(), False, None
+
+    def _poll(self):
+        n, h = self.nvml
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.reasons.update(k for k, bit in self.BITS.items() if r & bit)
+            except Exception:                            # noqa: BLE001 - a failed sample is just skipped
+                pass
+            time.sleep(0.01)
 
     def start(self):
+        try:
+            import pynvml as n
+            n.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+            ids = [v for v in vis.split(',') if v.strip().isdigit()]
+            phys = int(ids[self.index]) if self.index < len(ids) else self.index
+            h = n.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+            self.nvml = (n, h)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:                                # noqa: BLE001 - fall back to nvidia-smi
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
                                           '-lms', '50', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
@@ -203,6 +234,12 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(',')])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            sm = sorted(self.sm)
+            return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.mx,
+                    'reasons': sorted(self.reasons), 'samples': len(sm), 'source': 'nvml, 10 ms period'}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
@@ -212,7 +249,7 @@ class ClockSampler:
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith('active')})
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(sm)}
+                'reasons': reasons, 'samples': len(sm), 'source': 'nvidia-smi -lms 50'}
 
 
 def run_reference(args, rank, world):
@@ -246,7 +283,7 @@ def base_line(args, world, value, ms, impl='favae_b200'):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--batch', type=int, default=32, help='images per GPU')
     ap.add_argument('--impl', default='favae_b200', choices=['favae_b200', 'reference'])
