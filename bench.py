@@ -412,8 +412,8 @@ def main():
             'clocks': clocks,
             'roofline': {'kernel': 'ffl_kernel<256> (level-0 DSL spectrum loss, 128x256x256 maps per image)',
                          'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm'], 'unit': 'GB/s',
-                         'frac': achieved / pk['hbm'], 'traffic': 16.57 * e_l0, 'peak_source': pk['src'],
-                         'traffic_source': 'ncu --set full dram__bytes_read+write = 16.57 B/element incl. the L2 prefetch of the next map (profiles/ncu_r1_summary.md)',
+                         'frac': achieved / pk['hbm'], 'traffic': 15.48 * e_l0, 'peak_source': pk['src'],
+                         'traffic_source': 'ncu --set full dram__bytes_read+write = 15.48 B/element (gpurun_out/prof_ffl256_r1i; part of the last gradient writes is still in L2 when the kernel ends) (profiles/ncu_r1_summary.md)',
                          'algorithmic_bytes_per_launch': 16.0 * e_l0, 'ms_per_launch': l0_ms},
             'roofline_vq': {'kernel': 'favae_vq_search_tc: tcgen05 cta_group::2 search + exact re-score + fallback, '
                                       '16384 x 256 codebook; algorithmic 2*N*K*D flops',

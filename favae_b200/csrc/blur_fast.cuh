@@ -198,7 +198,9 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ /*aux*
 // Occupancy is what this kernel needs: with 3 rows of gy in flight (instead of 6) and the x row
 // requested in the iteration that uses it, the kernel fits 126 registers without spills, i.e. 4 CTAs
 // (16 warps) per SM: 0.88 ms at 4096 maps of 256^2 against 1.11 ms at 160 registers / 3 CTAs.
-// (Capping the 6-row version at 128 registers spilled: 1.29 ms; all rows unrolled 1.26 ms.)
+// (Capping the 6-row version at 128 registers spilled: 1.29 ms; all rows unrolled 1.26 ms.  The
+// remaining stall is the x row arriving late; two or more x rows in flight spill at 128 registers
+// (0.90 ms) and per-thread L2 prefetch hints a few rows ahead change nothing (0.80 ms).)
 #ifndef FAVAE_ADJSIG_MINB
 #define FAVAE_ADJSIG_MINB 4
 #endif
