@@ -182,6 +182,29 @@ def time_cpu(batch, steps, warmup):
     return batch * steps / dt, dt / steps * 1e3
 
 
+def bind_near_gpu(index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of
+    the end-to-end measurement are allocated on the NUMA node behind the GPU's PCIe root (with 8 ranks
+    the H2D streams otherwise cross the socket interconnect).  Returns the CPU count, or None."""
+    try:
+        import pynvml as n
+        n.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+        ids = [v for v in vis.split(',') if v.strip().isdigit()]
+        phys = int(ids[index]) if index < len(ids) else index
+        h = n.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = n.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:                                    # noqa: BLE001 - placement is an optimisation only
+        pass
+    return None
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region.  NVML is polled from a thread
     every 10 ms (no process start-up latency: a 50-step run lasts ~0.2 s); `nvidia-smi -lms` is the
@@ -349,6 +372,7 @@ def main():
     value = args.batch * world * 1e3 / ms_step
 
     # ---- end to end: pinned host inputs -> H2D -> step -> loss.item()
+    numa = bind_near_gpu(local)          # before the pinned allocation: first touch decides the NUMA node
     host = make_inputs(args.batch, 4321 + rank, device, pin=True)
     copy_stream = torch.cuda.Stream(device)
 
@@ -407,7 +431,7 @@ def main():
         line = base_line(args, world, value, ms_step)
         line.update({
             'e2e': {'value': e2e_value, 'unit': 'img/s', 'h2d_bytes_per_step': input_bytes(host),
-                    'd2h_bytes_per_step': 4, 'steps': n_e2e},
+                    'd2h_bytes_per_step': 4, 'steps': n_e2e, 'host_cpus_bound': numa},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {'kernel': 'ffl_kernel<256> (level-0 DSL spectrum loss, 128x256x256 maps per image)',
