@@ -340,13 +340,13 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
       float o[4], z[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        float2 a2 = pk_mul(pk_dup(k[P]), seg[c + P]);          // (sum k v, sum k v')
-        float za = dk[P] * seg[c + P].x;                        // sum k' v
+        float2 a2 = pk_mul(pk_dup(kd[P].x), seg[c + P]);       // (sum k v, sum k v')
+        float za = kd[P].y * seg[c + P].x;                      // sum k' v
 #pragma unroll
         for (int t = 0; t < P; ++t) {
           const float2 q = pk_add(seg[c + t], seg[c + KS - 1 - t]);
-          a2 = pk_fma(pk_dup(k[t]), q, a2);
-          za = fmaf(dk[t], q.x, za);
+          a2 = pk_fma(pk_dup(kd[t].x), q, a2);
+          za = fmaf(kd[t].y, q.x, za);
         }
         o[c] = a2.x; z[c] = a2.y + za;
       }
