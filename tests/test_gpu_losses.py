@@ -238,3 +238,27 @@ def test_f4_config_end_to_end_vs_oracle():
         sr = (xn_o[bad].double() * en_o[idx_o[bad]].double()).sum(-1)
         assert (sg - sr).abs().max() <= 1e-6 and bad.numel() <= 40
     assert zg.grad is not None and torch.isfinite(zg.grad).all()
+
+
+def test_blur_split_sigma_path_matches_fused():
+    """FAVAE_BLUR_SIGMA=split (plain adjoint + blur_sigma_kernel) is read once per process, so it
+    runs in a child process; its input gradient and sigma gradient must match the fused kernel's."""
+    import subprocess
+    import sys
+    code = (
+        "import torch, favae_b200\n"
+        "g = torch.Generator().manual_seed(7)\n"
+        "x = torch.randn(2, 3, 128, 128, generator=g).cuda().requires_grad_(True)\n"
+        "go = torch.randn(2, 3, 128, 128, generator=g).cuda()\n"
+        "s = torch.tensor(2.5, device='cuda', requires_grad=True)\n"
+        "(favae_b200.gaussian_blur_reflect(x, s, 9) * go).sum().backward()\n"
+        "print(repr(float(s.grad)), repr(float(x.grad.double().abs().sum())))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for mode in ('fused', 'split'):
+        env = dict(os.environ, FAVAE_BLUR_SIGMA=mode, PYTHONPATH=root)
+        r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append([float(v) for v in r.stdout.strip().splitlines()[-1].split()])
+    assert outs[0][0] == pytest.approx(outs[1][0], rel=1e-4)
+    assert outs[0][1] == pytest.approx(outs[1][1], rel=1e-5)
