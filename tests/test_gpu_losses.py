@@ -262,3 +262,47 @@ def test_blur_split_sigma_path_matches_fused():
         outs.append([float(v) for v in r.stdout.strip().splitlines()[-1].split()])
     assert outs[0][0] == pytest.approx(outs[1][0], rel=1e-4)
     assert outs[0][1] == pytest.approx(outs[1][1], rel=1e-5)
+
+
+def test_full_size_properties_level0():
+    """Size-independent properties at the BASELINE level-0 size (batch 32: 4096 maps of 256^2 per
+    tensor), where the oracle is too slow to run: spectrum-loss known-answer properties and the
+    adjoint / sigma-derivative identities of the blur."""
+    from favae_b200 import FocalFrequencyLoss, gaussian_blur_reflect
+    if torch.cuda.mem_get_info()[0] < 24 << 30:
+        pytest.skip('needs 24 GB of free device memory')
+    shape = (32, 128, 256, 256)
+    g = torch.Generator(device='cuda').manual_seed(123)
+    p = torch.randn(shape, device='cuda', generator=g).requires_grad_(True)
+    t = torch.randn(shape, device='cuda', generator=g).requires_grad_(True)
+    ffl = FocalFrequencyLoss(loss_weight=0.01)
+    loss = ffl(p, t)
+    loss.backward()
+    # gradient wrt target is minus the gradient wrt pred (the loss sees pred - target only)
+    assert torch.equal(t.grad, -p.grad)
+    # KAT3 Parseval bound (weights <= 1) and KAT5 quadratic scaling
+    with torch.no_grad():
+        d2 = float(((p - t) ** 2).mean())
+        assert 0.0 < float(loss) <= 0.01 * d2 * (1 + 1e-5)
+        assert float(ffl(t + 3.0 * (p - t), t)) == pytest.approx(9.0 * float(loss), rel=1e-4)
+        # the weight matrix is detached, so the gradient is that of the quadratic form sum w |D|^2:
+        # <grad, d> = 2 * loss (Euler's identity for a 2-homogeneous function of d = pred - target)
+        assert float((p.grad * (p - t)).sum()) == pytest.approx(2.0 * float(loss), rel=1e-3)
+    del t
+    p.grad = None
+    # blur: <blur(x), g> == <x, blur^T(g)>, and d/dsigma against a central difference
+    x = p.detach()
+    go = torch.randn(shape, device='cuda', generator=g)
+    xs = x.clone().requires_grad_(True)
+    sig = torch.tensor(3.0, device='cuda', requires_grad=True)
+    y = gaussian_blur_reflect(xs, sig, 9)
+    lhs = float((y.detach().double() * go.double()).sum())
+    (y * go).sum().backward()
+    rhs = float((xs.grad.double() * x.double()).sum())
+    assert lhs == pytest.approx(rhs, rel=1e-5, abs=1e-2)
+    with torch.no_grad():
+        h = 1e-2
+        yp = gaussian_blur_reflect(x, torch.tensor(3.0 + h, device='cuda'), 9)
+        ym = gaussian_blur_reflect(x, torch.tensor(3.0 - h, device='cuda'), 9)
+        fd = float(((yp.double() - ym.double()) * go.double()).sum()) / (2 * h)
+    assert float(sig.grad) == pytest.approx(fd, rel=5e-3, abs=1.0)
