@@ -402,7 +402,7 @@ def main():
 
     e2e_run(2)
     barrier()
-    n_e2e = max(2, min(args.steps, 5))
+    n_e2e = max(2, min(args.steps, 20))
     e0.record()
     e2e_run(n_e2e)
     e1.record()
