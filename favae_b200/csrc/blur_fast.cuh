@@ -199,8 +199,9 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ /*aux*
 // requested in the iteration that uses it, the kernel fits 126 registers without spills, i.e. 4 CTAs
 // (16 warps) per SM: 0.88 ms at 4096 maps of 256^2 against 1.11 ms at 160 registers / 3 CTAs.
 // (Capping the 6-row version at 128 registers spilled: 1.29 ms; all rows unrolled 1.26 ms.  The
-// remaining stall is the x row arriving late; two or more x rows in flight spill at 128 registers
-// (0.90 ms) and per-thread L2 prefetch hints a few rows ahead change nothing (0.80 ms).)
+// stall that remained was the x row (requested one iteration ahead into registers) arriving late;
+// two x rows in registers spill at the 128-register cap (0.90 ms), L2 prefetch hints change
+// nothing, so x now travels through a cp.async shared-memory ring 3 iterations ahead: 0.74 ms.)
 #ifndef FAVAE_ADJSIG_MINB
 #define FAVAE_ADJSIG_MINB 4
 #endif
@@ -241,6 +242,9 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
 #ifndef FAVAE_ADJSIG_XQ
 #define FAVAE_ADJSIG_XQ 1
 #endif
+#ifndef FAVAE_ADJSIG_XASYNC
+#define FAVAE_ADJSIG_XASYNC 4      // > 0: x rows through a cp.async shared ring of (up to) that many rows
+#endif
   constexpr int XQ = FAVAE_ADJSIG_XQ;
   constexpr int Q = FAVAE_ADJSIG_Q + ((XQ - (KS + FAVAE_ADJSIG_Q) % XQ) % XQ), RS = KS + Q, NR = TH + KS - 1;
   static_assert(RS % XQ == 0, "x prefetch ring must tile the unroll factor");
@@ -259,11 +263,32 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
     if (live && r >= KS - 1 && yo < h) xv = ld4(aux + mapoff + (long long)yo * w + x0);
     return xv;
   };
-  float4 ring[RS], xq[XQ];
+  float4 ring[RS];
 #pragma unroll
   for (int q = 0; q < RS; ++q) ring[q] = (q < Q) ? load_row(q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#if FAVAE_ADJSIG_XASYNC
+  // x rows travel HBM -> shared memory by cp.async, XD - 1 iterations ahead and without holding
+  // registers (one commit group per iteration, so wait_group XD - 1 means "the row of this iteration
+  // has landed"); each thread reads back only the 16 bytes it requested itself.
+  constexpr int XW = FAVAE_ADJSIG_XASYNC;        // wanted depth; the ring must tile the unroll factor
+  constexpr int XD = (XW >= 6 && RS % 6 == 0) ? 6 : (XW >= 4 && RS % 4 == 0) ? 4 : (RS % 3 == 0) ? 3 : 2;
+  static_assert(RS % XD == 0, "x ring must tile the unroll factor");
+  __shared__ float4 xring[XD][THREADS];
+  auto issue_x = [&](int r, int slot) {
+    const int yo = y0 + r - (KS - 1);
+    if (live && r >= KS - 1 && r < NR && yo < h) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(&xring[slot][threadIdx.x]);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(aux + mapoff + (long long)yo * w + x0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int q = 0; q < XD - 1; ++q) issue_x(q, q % XD);
+#else
+  float4 xq[XQ];
 #pragma unroll
   for (int q = 0; q < XQ; ++q) xq[q] = load_x(q);
+#endif
   constexpr int STEP = FAVAE_ADJSIG_FULL ? NR : RS;
 #pragma unroll 1
   for (int r0 = 0; r0 < NR; r0 += STEP) {
@@ -273,8 +298,12 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
       const int u = STEP == RS ? uu : uu % RS;
       if (r >= NR) break;
       if (r + Q < NR) ring[(u + Q) % RS] = load_row(r + Q);
+#if FAVAE_ADJSIG_XASYNC
+      issue_x(r + XD - 1, (uu + XD - 1) % XD);
+#else
       const float4 xrow = xq[u % XQ];
       if (r + XQ < NR) xq[u % XQ] = load_x(r + XQ);
+#endif
       {                                            // E, rows: doubled when the row enters the window
         const int ry = reflect_idx(y0 - P + r, h);
         if (ry == 0 || ry == h - 1) { float4& b = ring[u]; b.x *= 2.f; b.y *= 2.f; b.z *= 2.f; b.w *= 2.f; }
@@ -357,6 +386,10 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
       }
       if (live && yo < h) {
         *reinterpret_cast<float4*>(dst + mapoff + (long long)yo * w + x0) = make_float4(o[0], o[1], o[2], o[3]);
+#if FAVAE_ADJSIG_XASYNC
+        asm volatile("cp.async.wait_group %0;" ::"n"(XD - 1) : "memory");
+        const float4 xrow = xring[uu % XD][threadIdx.x];
+#endif
         acc_sigma = fmaf(xrow.x, z[0], fmaf(xrow.y, z[1], fmaf(xrow.z, z[2], fmaf(xrow.w, z[3], acc_sigma))));
       }
     }
