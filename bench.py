@@ -479,7 +479,7 @@ def time_vq_search(n_lat, device, iters=5):
     def run():
         _lib.call('favae_vq_search_tc', xh.data_ptr(), eh.data_ptr(), xn.data_ptr(), en.data_ptr(), n_lat, K_CODES,
                   DIM, ws.data_ptr(), nbytes, keys.data_ptr(), idx.data_ptr(), _lib.stream())
-    for _ in range(3):
+    for _ in range(20):
         run()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -491,7 +491,7 @@ def time_vq_search(n_lat, device, iters=5):
     return a.elapsed_time(b) / iters
 
 
-def time_blur(batch, device, iters=5):
+def time_blur(batch, device, iters=20):
     """Device time of the level-0 blur forward and backward (+ sigma gradient) kernels."""
     from favae_b200 import _lib
     shape = (batch, 128, 256, 256)
@@ -506,7 +506,7 @@ def time_blur(batch, device, iters=5):
                                       y.data_ptr(), _lib.stream())),
             ('bwd', lambda: _lib.call('favae_blur_backward', g.data_ptr(), x.data_ptr(), maps, 256, 256, KSIZE,
                                       sig.data_ptr(), y.data_ptr(), gs.data_ptr(), parts.data_ptr(), _lib.stream()))):
-        for _ in range(2):
+        for _ in range(20):                      # the e2e phase before this leaves the GPU mostly idle: let the clocks ramp up
             fn()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()

@@ -245,8 +245,16 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
 #ifndef FAVAE_ADJSIG_XASYNC
 #define FAVAE_ADJSIG_XASYNC 4      // > 0: x rows through a cp.async shared ring of (up to) that many rows
 #endif
+// gy AND x rows through cp.async shared-memory rings of that depth (a power of two; 0: register
+// prefetch).  Measured at 4096 maps of 256^2: register prefetch 0.79 ms, x ring only 0.74 ms, both
+// rings depth 4 0.66 ms, depth 8 0.68 ms (and 33 KB of static shared memory, over the 48 KB launch
+// limit together with the line buffers of the narrow maps).
+#ifndef FAVAE_ADJSIG_GASYNC
+#define FAVAE_ADJSIG_GASYNC 4
+#endif
   constexpr int XQ = FAVAE_ADJSIG_XQ;
-  constexpr int Q = FAVAE_ADJSIG_Q + ((XQ - (KS + FAVAE_ADJSIG_Q) % XQ) % XQ), RS = KS + Q, NR = TH + KS - 1;
+  constexpr int GD = FAVAE_ADJSIG_GASYNC;
+  constexpr int Q = GD ? 0 : FAVAE_ADJSIG_Q + ((XQ - (KS + FAVAE_ADJSIG_Q) % XQ) % XQ), RS = KS + Q, NR = TH + KS - 1;
   static_assert(RS % XQ == 0, "x prefetch ring must tile the unroll factor");
   const long long mapoff = map * (long long)h * w;
   auto load_row = [&](int r) -> float4 {
@@ -266,7 +274,29 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
   float4 ring[RS];
 #pragma unroll
   for (int q = 0; q < RS; ++q) ring[q] = (q < Q) ? load_row(q) : make_float4(0.f, 0.f, 0.f, 0.f);
-#if FAVAE_ADJSIG_XASYNC
+#if FAVAE_ADJSIG_GASYNC
+  // Both input streams travel HBM -> shared memory by cp.async, GD - 1 iterations ahead, holding no
+  // registers: one commit group per iteration carries the gy row that enters the window and the x row
+  // of that iteration's output, so wait_group GD - 1 means "this iteration's rows have landed".  Each
+  // thread reads back only the 16 bytes it requested itself.
+  static_assert((GD & (GD - 1)) == 0, "ring depth must be a power of two");
+  __shared__ float4 gring[GD][THREADS], xring[GD][THREADS];
+  auto issue_rows = [&](int r) {
+    if (live && r < NR) {
+      const int slot = r & (GD - 1);
+      const unsigned dg = (unsigned)__cvta_generic_to_shared(&gring[slot][threadIdx.x]);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dg), "l"(base + (long long)reflect_idx(y0 - P + r, h) * w + x0) : "memory");
+      const int yo = y0 + r - (KS - 1);
+      if (r >= KS - 1 && yo < h) {
+        const unsigned dx = (unsigned)__cvta_generic_to_shared(&xring[slot][threadIdx.x]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dx), "l"(aux + mapoff + (long long)yo * w + x0) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int q = 0; q < GD - 1; ++q) issue_rows(q);
+#elif FAVAE_ADJSIG_XASYNC
   // x rows travel HBM -> shared memory by cp.async, XD - 1 iterations ahead and without holding
   // registers (one commit group per iteration, so wait_group XD - 1 means "the row of this iteration
   // has landed"); each thread reads back only the 16 bytes it requested itself.
@@ -297,8 +327,15 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
       const int r = r0 + uu;
       const int u = STEP == RS ? uu : uu % RS;
       if (r >= NR) break;
+#if FAVAE_ADJSIG_GASYNC
+      issue_rows(r + GD - 1);
+      asm volatile("cp.async.wait_group %0;" ::"n"(GD - 1) : "memory");
+      ring[u] = live ? gring[r & (GD - 1)][threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+#else
       if (r + Q < NR) ring[(u + Q) % RS] = load_row(r + Q);
-#if FAVAE_ADJSIG_XASYNC
+#endif
+#if FAVAE_ADJSIG_GASYNC
+#elif FAVAE_ADJSIG_XASYNC
       issue_x(r + XD - 1, (uu + XD - 1) % XD);
 #else
       const float4 xrow = xq[u % XQ];
@@ -386,7 +423,9 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
       }
       if (live && yo < h) {
         *reinterpret_cast<float4*>(dst + mapoff + (long long)yo * w + x0) = make_float4(o[0], o[1], o[2], o[3]);
-#if FAVAE_ADJSIG_XASYNC
+#if FAVAE_ADJSIG_GASYNC
+        const float4 xrow = xring[r & (GD - 1)][threadIdx.x];
+#elif FAVAE_ADJSIG_XASYNC
         asm volatile("cp.async.wait_group %0;" ::"n"(XD - 1) : "memory");
         const float4 xrow = xring[uu % XD][threadIdx.x];
 #endif
