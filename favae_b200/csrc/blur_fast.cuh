@@ -116,7 +116,9 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ /*aux*
   // Register ring of RS = KS + Q rows: the KS-row window of the vertical pass plus Q rows in flight
   // from HBM (explicit prefetch: 6 rows per thread for the forward kernel, whose NR rows are all
   // unrolled; 3 for the adjoint, which trades prefetch depth for a fifth CTA per SM and unrolls RS
-  // rows inside a rolled loop).  Every ring index is a constant.
+  // rows inside a rolled loop).  Every ring index is a constant.  (A cp.async shared-memory ring as
+  // in blur_adjsig_kernel was measured here too: no gain for either mode - 0.474 / 0.393 ms against
+  // 0.469 / 0.394 ms - these two kernels are not waiting for their loads.)
 #ifndef FAVAE_ADJ_Q
 #define FAVAE_ADJ_Q 3
 #endif
