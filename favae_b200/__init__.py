@@ -14,12 +14,12 @@ from __future__ import annotations
 import sys
 
 from .focal_frequency_loss import FocalFrequencyLoss
-from .gaussian_blur import gaussian_blur_reflect, install_reference_blur
+from .gaussian_blur import LazyBlur, gaussian_blur_reflect, install_reference_blur, lazy_gaussian_blur
 from .l2_quantize import CosineSimCodebook, EuclideanCodebook, VectorQuantize
 from .vqgan_losses import recon_ffl_features_loss, recon_ffl_loss, recon_sl_gaussian_features_loss
 
 __all__ = ['VectorQuantize', 'CosineSimCodebook', 'EuclideanCodebook', 'FocalFrequencyLoss',
-           'gaussian_blur_reflect', 'recon_ffl_loss', 'recon_ffl_features_loss',
+           'gaussian_blur_reflect', 'lazy_gaussian_blur', 'LazyBlur', 'recon_ffl_loss', 'recon_ffl_features_loss',
            'recon_sl_gaussian_features_loss', 'patch_reference', 'build']
 
 __version__ = '0.1.0'
@@ -39,12 +39,21 @@ def patch_reference():
     * ``models.l2_quantize.VectorQuantize`` (+ codebook classes) are replaced
       (``models/vqgan_fcm.py:102``);
     * ``losses.vqgan_losses`` functions are replaced (``favae_scripts/train_favae.py:24``);
-    * every ``_gaussian_blur`` method in ``models.vqgan_fcm`` / ``models.codec`` is replaced.
+    * every ``_gaussian_blur`` method in ``models.vqgan_fcm`` / ``models.codec`` is replaced by
+      the deferred blur (``LazyBlur``), which ``recon_ffl_features_loss`` fuses with the spectrum
+      loss (``models/codec.py:284-309, 655-686, 978-999, 1105-1123``, ``models/vqgan_fcm.py:131-134``).
     """
     from . import focal_frequency_loss as ffl_mod
     from . import l2_quantize as q_mod
     from . import vqgan_losses as l_mod
-    sys.modules.setdefault('focal_frequency_loss', ffl_mod)
+    prev = sys.modules.get('focal_frequency_loss')
+    if prev is not None and prev is not ffl_mod and \
+            getattr(prev, 'FocalFrequencyLoss', None) is not ffl_mod.FocalFrequencyLoss:
+        import warnings
+        warnings.warn('favae_b200.patch_reference(): the pip package focal_frequency_loss was already imported; '
+                      'it is replaced in sys.modules, but names bound by earlier `from focal_frequency_loss '
+                      'import FocalFrequencyLoss` statements still point at the pip class', stacklevel=2)
+    sys.modules['focal_frequency_loss'] = ffl_mod
     done = ['focal_frequency_loss']
     try:
         import models.l2_quantize as ref_q

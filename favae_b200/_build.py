@@ -73,11 +73,13 @@ def build(force=False, verbose=True):
     os.makedirs(OBJ, exist_ok=True)
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(_compile, sources()))
-    cmd = [_nvcc(), '-shared', '-o', LIB, *objs, '-cudart', 'static', '-Xlinker', '--no-undefined',
-           '-lpthread', '-ldl', '-lrt']
+    tmp = f'{LIB}.{os.getpid()}.tmp'           # link under a private name, then rename atomically:
+    cmd = [_nvcc(), '-shared', '-o', tmp, *objs, '-cudart', 'static', '-Xlinker', '--no-undefined',
+           '-lpthread', '-ldl', '-lrt']          # nobody can dlopen a half-written library
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
+    os.replace(tmp, LIB)
     with open(STAMP, 'w') as fh:
         fh.write(_source_digest())
     if verbose:

@@ -6,7 +6,9 @@ anywhere in favae_b200/) imports ``oracle/`` or computes on the CPU.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
+import fcntl
 import os
 import threading
 
@@ -30,8 +32,8 @@ SIGNATURES = {
     'favae_vq_search_tc': (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp, _sz, _vp, _vp, _vp]),
     'favae_vq_search_tc_overflow_rows': (_i32, [_vp, _i64, _i64, _i32, _vp]),
     'favae_vq_gather_st': (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
-    'favae_vq_code_stats': (_i32, [_vp, _vp, _i64, _i64, _i32, _vp, _vp]),
-    'favae_vq_ema_update_cosine': (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp]),
+    'favae_vq_code_stats': (_i32, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
+    'favae_vq_ema_update_cosine': (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp]),
     'favae_vq_ema_update_euclid': (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _vp, _vp]),
     'favae_vq_backward': (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _vp, _vp]),
     'favae_vq_gather_rows': (_i32, [_vp, _vp, _i64, _i64, _i32, _i64, _vp, _vp]),
@@ -41,7 +43,9 @@ SIGNATURES = {
     'favae_scale_inplace': (_i32, [_vp, _vp, _i64, _vp, _vp]),
     'favae_blur_forward': (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
     'favae_blur_partials': (_i64, [_i64, _i32, _i32]),
-    'favae_blur_backward': (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    'favae_blur_backward': (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _vp, _vp]),
+    'favae_blur_fast_supported': (_i32, [_i32, _i32, _i32]),
+    'favae_blur_diff_forward': (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
 }
 
 
@@ -56,12 +60,21 @@ def load():
         if _lib is not None:
             return _lib
         if _build.needs_build():
-            _build.build(verbose=False)
+            # every rank of a DDP / accelerate job gets here at once: serialise the build across
+            # PROCESSES with a file lock (the winner builds to a temporary name and renames it,
+            # _build.build), and re-check once the lock is held
+            with open(os.path.join(_build.HERE, '.build.lock'), 'w') as lock:
+                fcntl.flock(lock, fcntl.LOCK_EX)
+                try:
+                    if _build.needs_build():
+                        _build.build(verbose=False)
+                finally:
+                    fcntl.flock(lock, fcntl.LOCK_UN)
         lib = ctypes.CDLL(_build.LIB)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError if the ABI lost a symbol
             fn.restype, fn.argtypes = res, args
-        if lib.favae_abi_version() != 1:
+        if lib.favae_abi_version() != 2:
             raise RuntimeError('favae_b200: ABI version mismatch, rebuild the library')
         _lib = lib
         return lib
@@ -72,8 +85,32 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def stream():
-    return torch.cuda.current_stream().cuda_stream
+def stream(device=None):
+    """Raw handle of torch's current stream on ``device`` (default: the current device)."""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+_NULL = contextlib.nullcontext()
+
+
+def on_device_of(*tensors):
+    """Context that makes the tensors' device the current one for the launches inside it, after
+    checking that they all live on ONE CUDA device.  (The C ABI launches on the current device and
+    ``stream()`` returns that device's current stream; a tensor on cuda:1 while cuda:0 is current
+    would otherwise be handed to a kernel on the wrong device.)"""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError('favae_b200 runs on CUDA tensors only (there is no CPU path)')
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f'favae_b200: tensors on different devices ({dev} and {t.device})')
+    if dev is None or dev.index == torch.cuda.current_device():
+        return _NULL
+    return torch.cuda.device(dev)
 
 
 def call(name: str, *args):
@@ -84,13 +121,14 @@ def call(name: str, *args):
 
 
 def require_cuda(*tensors):
+    """Only the device is checked here: half / bfloat16 inputs (autocast) are cast with ``.float()``
+    by the callers, as the reference does (l2_quantize.py:393,266 ``x.float()`` under
+    ``autocast(enabled=False)``), so autograd casts the gradient back."""
     for t in tensors:
         if t is None:
             continue
         if not t.is_cuda:
             raise RuntimeError('favae_b200 runs on CUDA tensors only (there is no CPU path)')
-        if t.dtype != torch.float32 and t.dtype != torch.int64:
-            raise RuntimeError(f'favae_b200 expects float32 tensors, got {t.dtype}')
 
 
 def launch_count() -> int:

@@ -90,7 +90,7 @@ template <int KS, int TH, int MODE>
 __global__ void __launch_bounds__(THREADS, MODE == MODE_ADJ ? FAVAE_ADJ_MINB : FAVAE_FWD_MINB)
 blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ /*aux*/, int h, int w, long long items,
                  int strips, const float* __restrict__ sigma, float* __restrict__ dst,
-                 float* __restrict__ /*partials*/) {
+                 float* __restrict__ /*partials*/, float oscale) {
   // src: x (FWD) or gy (ADJ); dst: y / gx
   static_assert(MODE == MODE_FWD || MODE == MODE_ADJ, "sigma-gradient modes have their own kernels");
   constexpr int P = KS / 2;
@@ -180,11 +180,109 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ /*aux*
       for (int t = 0; t < KS; ++t) o[c] = fmaf(k[t], seg[c + t], o[c]);
     }
     if (ADJ) {
-      const float dr = (yo == 0 || yo == h - 1) ? 0.5f : 1.f;   // D, rows
+      const float dr = ((yo == 0 || yo == h - 1) ? 0.5f : 1.f) * oscale;   // D, rows (and the caller's scale)
       o[0] *= dr * d0; o[1] *= dr; o[2] *= dr; o[3] *= dr * d3;
     }
     if (live && yo < h)
       *reinterpret_cast<float4*>(dst + mapoff + (long long)yo * w + x0) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// d = B_dec(dec) - B_enc(enc): the blurred pair of the DSL (models/vqgan_fcm.py:131-134 and the codec
+// call sites, consumed only by ffl(de, en), losses/vqgan_losses.py:25) written as ONE map.  The spectrum
+// loss sees pred - target only, so the two blurred maps never need to exist: 12 B/element (read enc, read
+// dec, write d) instead of 16 for two blurs, and the loss kernel then reads 4 B/element instead of 8.
+// Same pipeline as blur_fast_kernel<MODE_FWD>, run twice over the strip by the same threads: pass 0 leaves
+// B_enc(enc) in dst, pass 1 computes B_dec(dec) and subtracts what the thread itself stored (each thread
+// re-reads exactly its own 16 bytes per row, so program order makes the store visible; the strip is 32 KB
+// and still sits in L2).  No shared strip buffer (64 KB per CTA would cost two of the five CTAs per SM)
+// and no second register ring.
+template <int KS, int TH>
+__global__ void __launch_bounds__(THREADS, FAVAE_FWD_MINB)
+blur_diff_kernel(const float* __restrict__ enc, const float* __restrict__ dec, int h, int w, long long items,
+                 int strips, const float* __restrict__ sigma_enc, const float* __restrict__ sigma_dec,
+                 float* dst) {
+  constexpr int P = KS / 2;
+  extern __shared__ float lines[];               // [2 buffers][groups][w + 2*LPAD]
+  __shared__ float sk[2][32], sdk[32];
+  float k[KS], dk[KS];
+  load_weights<KS>(sigma_enc, sk[0], sdk, k, dk);
+  load_weights<KS>(sigma_dec, sk[1], sdk, k, dk);
+
+  const int tpi = w >> 2;
+  const int groups = THREADS / tpi;
+  const int grp = threadIdx.x / tpi, tx = threadIdx.x % tpi;
+  const int x0 = tx * 4;
+  const int ll = w + 2 * LPAD;
+  const long long item = (long long)blockIdx.x * groups + grp;
+  const bool live = item < items;
+  const long long map = live ? item / strips : 0;
+  const int y0_ = live ? (int)(item % strips) * TH : 0;
+  const long long mapoff = map * (long long)h * w;
+  constexpr int Q = FAVAE_FWD_Q, RS = KS + Q, NR = TH + KS - 1;
+
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    const float* base = (which ? dec : enc) + mapoff;
+    float* dbase = dst + mapoff;
+    int y0 = y0_;
+    // opaque per pass: otherwise the row offsets and output addresses of all 40 unrolled rows are
+    // hoisted out of this rolled loop as invariants and spill
+    asm volatile("" : "+l"(dbase), "+r"(y0));
+#pragma unroll
+    for (int t = 0; t < KS; ++t) k[t] = sk[which][t];
+    auto load_row = [&](int r) -> float4 {
+      const int ry = reflect_idx(y0 - P + r, h);
+      float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) in = ld4(base + (long long)ry * w + x0);
+      return in;
+    };
+    float4 ring[RS];
+#pragma unroll
+    for (int q = 0; q < RS; ++q) ring[q] = (q < Q) ? load_row(q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int u = r % RS;
+      if (r + Q < NR) ring[(u + Q) % RS] = load_row(r + Q);
+      if (r < KS - 1) continue;
+      const int yo = y0 + r - (KS - 1);
+      const bool store = live && yo < h;
+      float* out = dbase + (long long)yo * w + x0;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int t = 0; t < KS; ++t) fma4(v, k[t], ring[(u + RS - (KS - 1) + t) % RS]);
+      float* line = lines + (size_t)((r & 1) * groups + grp) * ll;
+      *reinterpret_cast<float4*>(line + LPAD + x0) = v;
+      {
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int j = x0 + c;
+          if (j >= 1 && j <= P) line[LPAD - j] = vv[c];
+          const int jr = w - 1 - j;
+          if (jr >= 1 && jr <= P) line[LPAD + w - 1 + jr] = vv[c];
+        }
+      }
+      __syncthreads();
+      // B_enc(enc) of this row, stored by this thread in pass 0.  Requested here, behind the barrier
+      // (an asm volatile load stays put: hoisted to the top of the unrolled strip, 32 of them spill),
+      // and consumed after the horizontal pass.
+      float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (which && store)
+        asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(prev.x), "=f"(prev.y), "=f"(prev.z), "=f"(prev.w) : "l"(out) : "memory");
+      float seg[4 + 2 * P];
+#pragma unroll
+      for (int i = 0; i < 4 + 2 * P; ++i) seg[i] = line[LPAD + x0 - P + i];
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int t = 0; t < KS; ++t) o[c] = fmaf(k[t], seg[c + t], o[c]);
+      }
+      if (store) *reinterpret_cast<float4*>(out) = make_float4(o[0] - prev.x, o[1] - prev.y, o[2] - prev.z, o[3] - prev.w);
+    }
+    __syncthreads();                              // the line buffers are reused by the second pass
   }
 }
 
@@ -214,7 +312,9 @@ template <int KS, int TH>
 __global__ void __launch_bounds__(THREADS, FAVAE_ADJSIG_MINB)
 blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux, int h, int w, long long items,
                    int strips, const float* __restrict__ sigma, float* __restrict__ dst,
-                   float* __restrict__ partials) {
+                   float* __restrict__ partials, float oscale) {
+  // oscale multiplies gx and the sigma partials (the fused DSL op feeds +G to the decoder side and -G
+  // to the encoder side, vqgan_losses.py:25: ffl(de, en)); it rides on the D row scaling
   constexpr int P = KS / 2;
   extern __shared__ float lines[];               // as float2: [2 buffers][groups][w + 2*LPAD]
   __shared__ float sk[32], sdk[32];
@@ -419,7 +519,7 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
         o[c] = a2.x; z[c] = a2.y + za;
       }
       {
-        const float dr = (yo == 0 || yo == h - 1) ? 0.5f : 1.f;   // D, rows
+        const float dr = ((yo == 0 || yo == h - 1) ? 0.5f : 1.f) * oscale;   // D, rows (and the caller's scale)
         o[0] *= dr * d0; o[1] *= dr; o[2] *= dr; o[3] *= dr * d3;
         z[0] *= dr * d0; z[1] *= dr; z[2] *= dr; z[3] *= dr * d3;
       }
@@ -623,34 +723,61 @@ inline long long num_blocks(long long maps, int h, int w, int mode = MODE_FWD) {
 
 template <int KS, int TH, int MODE>
 static int launch_one(const float* src, const float* aux, long long maps, int h, int w, const float* sigma,
-                      float* dst, float* partials, cudaStream_t s) {
+                      float* dst, float* partials, cudaStream_t s, float oscale) {
   const int strips = (h + TH - 1) / TH, groups = THREADS / (w / 4);
   const long long items = maps * strips;
   const long long blocks = (items + groups - 1) / groups;
   const size_t smem = sizeof(float) * 2 * groups * ((MODE == MODE_ADJ_SIG || MODE == MODE_SIGMA) ? 2 : 1) * (size_t)(w + 2 * LPAD);
   if constexpr (MODE == MODE_ADJ_SIG)
-    blur_adjsig_kernel<KS, TH><<<(unsigned)blocks, THREADS, smem, s>>>(src, aux, h, w, items, strips, sigma, dst, partials);
+    blur_adjsig_kernel<KS, TH><<<(unsigned)blocks, THREADS, smem, s>>>(src, aux, h, w, items, strips, sigma, dst, partials, oscale);
   else if constexpr (MODE == MODE_SIGMA)
     blur_sigma_kernel<KS, TH><<<(unsigned)blocks, THREADS, smem, s>>>(src, aux, h, w, items, strips, sigma, partials);
   else
     blur_fast_kernel<KS, TH, MODE><<<(unsigned)blocks, THREADS, smem, s>>>(src, aux, h, w, items, strips, sigma, dst,
-                                                                        partials);
+                                                                        partials, oscale);
   return check_launch("blur_fast");
+}
+
+template <int KS, int TH>
+static int launch_diff_one(const float* enc, const float* dec, long long maps, int h, int w, const float* sigma_enc,
+                           const float* sigma_dec, float* dst, cudaStream_t s) {
+  const int strips = (h + TH - 1) / TH, groups = THREADS / (w / 4);
+  const long long items = maps * strips;
+  const long long blocks = (items + groups - 1) / groups;
+  const size_t smem = sizeof(float) * 2 * groups * (size_t)(w + 2 * LPAD);
+  blur_diff_kernel<KS, TH><<<(unsigned)blocks, THREADS, smem, s>>>(enc, dec, h, w, items, strips, sigma_enc, sigma_dec, dst);
+  return check_launch("blur_diff");
+}
+static int launch_diff(const float* enc, const float* dec, long long maps, int h, int w, int ks, const float* sigma_enc,
+                       const float* sigma_dec, float* dst, cudaStream_t s) {
+#define FAVAE_BLUR_CASE(KS)                                                                                   \
+  case KS:                                                                                                    \
+    return h <= 16 ? launch_diff_one<KS, 16>(enc, dec, maps, h, w, sigma_enc, sigma_dec, dst, s)               \
+                   : launch_diff_one<KS, 32>(enc, dec, maps, h, w, sigma_enc, sigma_dec, dst, s);
+  switch (ks) {
+    FAVAE_BLUR_CASE(3)
+    FAVAE_BLUR_CASE(5)
+    FAVAE_BLUR_CASE(9)
+    FAVAE_BLUR_CASE(11)
+    FAVAE_BLUR_CASE(15)
+  }
+#undef FAVAE_BLUR_CASE
+  return fail(-22, "favae_b200: %s", "blur_diff: unsupported kernel size");
 }
 
 template <int MODE>
 static int launch(const float* src, const float* aux, long long maps, int h, int w, int ks, const float* sigma,
-                  float* dst, float* partials, cudaStream_t s) {
+                  float* dst, float* partials, cudaStream_t s, float oscale = 1.0f) {
 #define FAVAE_BLUR_CASE(KS)                                                                         \
   case KS:                                                                                          \
     if (MODE == MODE_ADJ_SIG && strip_rows(h, MODE) == FAVAE_ADJSIG_TH)                             \
-      return launch_one<KS, (MODE == MODE_ADJ_SIG ? FAVAE_ADJSIG_TH : 32), MODE>(src, aux, maps, h, w, sigma, dst, partials, s); \
+      return launch_one<KS, (MODE == MODE_ADJ_SIG ? FAVAE_ADJSIG_TH : 32), MODE>(src, aux, maps, h, w, sigma, dst, partials, s, oscale); \
     if (MODE == MODE_FWD && FAVAE_FWD_TH > 32 && strip_rows(h, MODE) == FAVAE_FWD_TH)               \
-      return launch_one<KS, (MODE == MODE_FWD ? FAVAE_FWD_TH : 32), MODE>(src, aux, maps, h, w, sigma, dst, partials, s); \
+      return launch_one<KS, (MODE == MODE_FWD ? FAVAE_FWD_TH : 32), MODE>(src, aux, maps, h, w, sigma, dst, partials, s, oscale); \
     if (MODE == MODE_ADJ && strip_rows(h, MODE) == FAVAE_ADJ_TH)                                    \
-      return launch_one<KS, (MODE == MODE_ADJ ? FAVAE_ADJ_TH : 32), MODE>(src, aux, maps, h, w, sigma, dst, partials, s); \
-    return strip_rows(h, MODE) == 16 ? launch_one<KS, 16, MODE>(src, aux, maps, h, w, sigma, dst, partials, s) \
-                                     : launch_one<KS, 32, MODE>(src, aux, maps, h, w, sigma, dst, partials, s);
+      return launch_one<KS, (MODE == MODE_ADJ ? FAVAE_ADJ_TH : 32), MODE>(src, aux, maps, h, w, sigma, dst, partials, s, oscale); \
+    return strip_rows(h, MODE) == 16 ? launch_one<KS, 16, MODE>(src, aux, maps, h, w, sigma, dst, partials, s, oscale) \
+                                     : launch_one<KS, 32, MODE>(src, aux, maps, h, w, sigma, dst, partials, s, oscale);
   switch (ks) {
     FAVAE_BLUR_CASE(3)
     FAVAE_BLUR_CASE(5)

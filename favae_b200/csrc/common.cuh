@@ -41,12 +41,25 @@ inline int check_launch(const char* what) {
     if (!(cond)) return favae::fail(-22, "favae_b200: %s", msg);  \
   } while (0)
 
+// Lazily computed launch state (cudaFuncSetAttribute done, resident cluster count, SM count) is
+// per DEVICE: a process may drive several GPUs, so every such cache is an array indexed by the
+// current device ordinal (one writer per device: the ABI is called from one thread per device).
+constexpr int MAX_DEVICES = 64;
+inline int device_ordinal() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) dev = 0;
+  return dev;
+}
+template <class T> struct PerDevice {
+  T v[MAX_DEVICES] = {};
+  T& here() { return v[device_ordinal()]; }
+};
+
 inline int num_sms() {
-  static int sms = 0;
+  static PerDevice<int> cache;
+  int& sms = cache.here();
   if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_ordinal());
     if (sms <= 0) sms = 148;
   }
   return sms;

@@ -58,10 +58,11 @@ FAVAE_HD void ffl_issue_loads(Env& env, const FflParams& p, long long batch, int
       const int f = t + TG * j;                          // float4 index inside the row
       r.pa[j] = r.ta[j] = r.pb[j] = r.tb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (live) {
+        // target == nullptr: pred already holds the difference map (fused DSL op, blur_diff_kernel)
         r.pa[j] = *reinterpret_cast<const float4*>(p.pred + base + 4 * f);
-        r.ta[j] = *reinterpret_cast<const float4*>(p.target + base + 4 * f);
+        if (p.target) r.ta[j] = *reinterpret_cast<const float4*>(p.target + base + 4 * f);
         r.pb[j] = *reinterpret_cast<const float4*>(p.pred + base + HALF * N + 4 * f);
-        r.tb[j] = *reinterpret_cast<const float4*>(p.target + base + HALF * N + 4 * f);
+        if (p.target) r.tb[j] = *reinterpret_cast<const float4*>(p.target + base + HALF * N + 4 * f);
       }
     }
   });
@@ -165,13 +166,15 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
         const long long nmaps = (p.maps - next_batch * MPC < MPC) ? p.maps - next_batch * MPC : MPC;
         if constexpr (C == 1) {
           env.prefetch_l2(p.pred + next_batch * MPC * (long long)(N * N), nmaps * N * N * sizeof(float));
-          env.prefetch_l2(p.target + next_batch * MPC * (long long)(N * N), nmaps * N * N * sizeof(float));
+          if (p.target) env.prefetch_l2(p.target + next_batch * MPC * (long long)(N * N), nmaps * N * N * sizeof(float));
         } else {
           const long long base = next_batch * (long long)(N * N) + (long long)cta * GPC * N;
           env.prefetch_l2(p.pred + base, GPC * N * sizeof(float));
           env.prefetch_l2(p.pred + base + HALF * N, GPC * N * sizeof(float));
-          env.prefetch_l2(p.target + base, GPC * N * sizeof(float));
-          env.prefetch_l2(p.target + base + HALF * N, GPC * N * sizeof(float));
+          if (p.target) {
+            env.prefetch_l2(p.target + base, GPC * N * sizeof(float));
+            env.prefetch_l2(p.target + base + HALF * N, GPC * N * sizeof(float));
+          }
         }
       }
     });

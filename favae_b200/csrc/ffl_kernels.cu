@@ -144,7 +144,8 @@ ffl_kernel(const FflParams p) {
 }
 
 template <class Cfg, bool FAST> static int launch_ffl_impl(const FflParams& p, cudaStream_t stream) {
-  static bool configured = false;
+  static PerDevice<bool> configured_dev;
+  bool& configured = configured_dev.here();
   auto kern = ffl_kernel<Cfg, FAST>;
   if (!configured) {
     FAVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -164,7 +165,8 @@ template <class Cfg, bool FAST> static int launch_ffl_impl(const FflParams& p, c
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // persistent grid: exactly the clusters that can be co-resident
-  static int resident = 0;
+  static PerDevice<int> resident_dev;
+  int& resident = resident_dev.here();
   if (!resident) {
     int per_sm = (int)(232448 / (Cfg::SMEM_BYTES + 1024));
     if (per_sm < 1) per_sm = 1;
@@ -204,7 +206,8 @@ int favae_ffl_forward(const float* pred, const float* target, int64_t maps, int 
                       float* grad_pred, float* grad_target, float* map_max,
                       const float* fmax_override, void* stream) {
   using namespace favae;
-  FAVAE_REQUIRE(pred && target && map_loss, "ffl_forward: null pointer");
+  FAVAE_REQUIRE(pred && map_loss, "ffl_forward: null pointer");
+  FAVAE_REQUIRE(target || !grad_target, "ffl_forward: a gradient for a target that was not given");
   FAVAE_REQUIRE(favae_ffl_supported(h, w), "ffl_forward: maps must be square, side a power of two in [8,512]");
   FAVAE_REQUIRE(maps >= 0, "ffl_forward: negative map count");
   FAVAE_REQUIRE((((uintptr_t)pred | (uintptr_t)target | (uintptr_t)grad_pred | (uintptr_t)grad_target) & 15) == 0,

@@ -253,12 +253,51 @@ vq_code_stats_kernel(const float* __restrict__ xn, const long long* __restrict__
   }
 }
 
+// Deterministic variant (FAVAE_VQ_DETERMINISTIC=1): one warp per CODE scans the index vector (L2
+// resident: 8 bytes per latent) and adds the rows of its members in ascending latent order, so bins
+// and embed_sum are bit-reproducible from run to run and independent of the launch geometry (the
+// atomic kernel above adds in arrival order: ~1e-7 relative noise that the EMA feeds into the next
+// search).  No zero-fill needed: every element of stats is written exactly once.
+__global__ void __launch_bounds__(256)
+vq_code_stats_det_kernel(const float* __restrict__ xn, const long long* __restrict__ idx, long long n,
+                         long long k, int d, float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const long long code = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (code >= k) return;
+  constexpr int MAXV = 8;                            // d <= 256 in registers; larger d in column chunks
+  for (int c0 = 0; c0 < d; c0 += 32 * MAXV) {
+    float acc[MAXV];
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) acc[j] = 0.f;
+    float count = 0.f;
+    for (long long r0 = 0; r0 < n; r0 += 32) {
+      const long long r = r0 + lane;
+      const bool hit = r < n && idx[r] == code;
+      unsigned m = __ballot_sync(0xffffffffu, hit);
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const float* src = xn + (r0 + b) * d + c0;
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j)
+          if (c0 + lane + 32 * j < d) acc[j] += src[lane + 32 * j];
+        count += 1.0f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j)
+      if (c0 + lane + 32 * j < d) stats[k + code * d + c0 + lane + 32 * j] = acc[j];
+    if (c0 == 0 && lane == 0) stats[code] = count;
+  }
+}
+
 // ----------------------------------------------------------------------------------
 // EMA update of the cosine codebook (one warp per code).          l2_quantize.py:421-438
 // ----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-vq_ema_cosine_kernel(float* __restrict__ embed, float* __restrict__ cluster, const float* __restrict__ en,
-                     const float* __restrict__ stats, long long k, int d, float decay) {
+vq_ema_cosine_kernel(float* __restrict__ embed, float* __restrict__ cluster, const float* en,
+                     const float* __restrict__ stats, long long k, int d, float decay,
+                     float* en_next, __half* __restrict__ eh_next) {
   const int lane = threadIdx.x & 31;
   const long long code = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (code >= k) return;
@@ -269,15 +308,31 @@ vq_ema_cosine_kernel(float* __restrict__ embed, float* __restrict__ cluster, con
   float* e = embed + code * d;
   if (bins == 0.0f) {
     for (int c = lane; c < d; c += 32) e[c] = e[c] * decay + en[code * d + c] * one_minus;
-    return;
+  } else {
+    float ss = 0.f;
+    for (int c = lane; c < d; c += 32) { const float v = es[c] / bins; ss += v * v; }
+    ss = warp_sum(ss);
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+    for (int c = lane; c < d; c += 32) {
+      const float v = (es[c] / bins) / denom;
+      e[c] = e[c] * decay + v * one_minus;
+    }
   }
-  float ss = 0.f;
-  for (int c = lane; c < d; c += 32) { const float v = es[c] / bins; ss += v * v; }
-  ss = warp_sum(ss);
-  const float denom = fmaxf(sqrtf(ss), 1e-12f);
-  for (int c = lane; c < d; c += 32) {
-    const float v = (es[c] / bins) / denom;
-    e[c] = e[c] * decay + v * one_minus;
+  if (en_next || eh_next) {
+    // The next search needs l2norm(new code) (fp32, and 16x that in fp16): emitted here, with the
+    // arithmetic of vq_prepare_rows_kernel (same lane-strided sum, same shuffle tree, same division),
+    // so a cached row is bit-identical to a freshly prepared one.  en_next may alias en: each warp
+    // has finished reading its row of en above and writes only that row (the lanes re-read their own
+    // stores of e).
+    float ss = 0.f;
+    for (int c = lane; c < d; c += 32) { const float v = e[c]; ss += v * v; }
+    ss = warp_sum(ss);
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+    for (int c = lane; c < d; c += 32) {
+      const float v = e[c] / denom;
+      if (en_next) en_next[code * d + c] = v;
+      if (eh_next) eh_next[code * d + c] = __float2half_rn(v * 16.0f);
+    }
   }
 }
 
@@ -344,7 +399,8 @@ int favae_vq_prepare_rows(const float* x, int64_t n, int d, int64_t hw, int norm
   if (n == 0) return 0;
   const size_t smem = sizeof(float) * PREP_ROWS * (size_t)(d + 1);
   FAVAE_REQUIRE(smem <= 200 * 1024, "vq_prepare_rows: d too large");
-  static size_t configured = 0;
+  static PerDevice<size_t> configured_dev;
+  size_t& configured = configured_dev.here();
   if (smem > 48 * 1024 && smem > configured) {
     FAVAE_CUDA_OK(cudaFuncSetAttribute(vq_prepare_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -393,7 +449,8 @@ int favae_vq_gather_st(const float* x, const float* embed, const int64_t* idx, i
   }
   const size_t smem = sizeof(float) * PREP_ROWS * (size_t)(d + 1);
   FAVAE_REQUIRE(smem <= 200 * 1024, "vq_gather_st: d too large");
-  static size_t configured = 0;
+  static PerDevice<size_t> configured_dev;
+  size_t& configured = configured_dev.here();
   if (smem > 48 * 1024 && smem > configured) {
     FAVAE_CUDA_OK(cudaFuncSetAttribute(vq_gather_st_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
@@ -413,9 +470,13 @@ int favae_vq_gather_rows(const float* embed, const int64_t* idx, int64_t n, int6
 }
 
 int favae_vq_code_stats(const float* xn, const int64_t* idx, int64_t n, int64_t k, int d,
-                        float* stats, void* stream) {
+                        int deterministic, float* stats, void* stream) {
   FAVAE_REQUIRE(xn && idx && stats && n >= 0 && k > 0 && d > 0, "vq_code_stats: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
+  if (deterministic && n > 0) {
+    vq_code_stats_det_kernel<<<(unsigned)((k + 7) / 8), 256, 0, s>>>(xn, (const long long*)idx, n, k, d, stats);
+    return check_launch("vq_code_stats_det");
+  }
   FAVAE_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(float) * (size_t)k * (size_t)(d + 1), s));
   if (n == 0) return 0;
   long long blocks = (n + 7) / 8;
@@ -425,10 +486,10 @@ int favae_vq_code_stats(const float* xn, const int64_t* idx, int64_t n, int64_t 
 }
 
 int favae_vq_ema_update_cosine(float* embed, float* cluster_size, const float* en, const float* stats,
-                               int64_t k, int d, float decay, void* stream) {
+                               int64_t k, int d, float decay, float* en_next, void* eh_next, void* stream) {
   FAVAE_REQUIRE(embed && cluster_size && en && stats && k > 0 && d > 0, "vq_ema_update_cosine: bad arguments");
-  vq_ema_cosine_kernel<<<(unsigned)((k + 7) / 8), 256, 0, (cudaStream_t)stream>>>(embed, cluster_size, en,
-                                                                                stats, k, d, decay);
+  vq_ema_cosine_kernel<<<(unsigned)((k + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      embed, cluster_size, en, stats, k, d, decay, en_next, (__half*)eh_next);
   return check_launch("vq_ema_update_cosine");
 }
 

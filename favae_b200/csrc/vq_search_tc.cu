@@ -633,7 +633,31 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// TMA descriptors are built lazily and cached by (base pointer, rows, d, box): the codebook's fp16
+// image and the per-shape latent scratch keep their addresses from call to call, so a training loop
+// encodes each descriptor once.  A descriptor holds no data, only the address and
+// the geometry, so a stale entry is harmless as long as the key matches.  Small direct-mapped table,
+// one per thread (the ABI is called from one thread per device).
+struct MapKey { const void* base; long long rows; int d, box; };
+struct MapSlot { MapKey key; CUtensorMap map; bool used; };
+static int make_map_uncached(CUtensorMap* map, const void* base, long long rows, int d, int box_rows);
 static int make_map(CUtensorMap* map, const void* base, long long rows, int d, int box_rows) {
+  constexpr int SLOTS = 16;
+  static thread_local MapSlot cache[SLOTS] = {};
+  const size_t hsh = ((size_t)(uintptr_t)base >> 8) * 0x9E3779B97F4A7C15ull ^ (size_t)rows * 31u ^ (size_t)box_rows;
+  MapSlot& sl = cache[(hsh >> 20) % SLOTS];
+  if (sl.used && sl.key.base == base && sl.key.rows == rows && sl.key.d == d && sl.key.box == box_rows) {
+    *map = sl.map;
+    return 0;
+  }
+  int rc = make_map_uncached(map, base, rows, d, box_rows);
+  if (rc) return rc;
+  sl.key = MapKey{base, rows, d, box_rows};
+  sl.map = *map;
+  sl.used = true;
+  return 0;
+}
+static int make_map_uncached(CUtensorMap* map, const void* base, long long rows, int d, int box_rows) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(-38, "favae_b200: %s", "cuTensorMapEncodeTiled is unavailable");
   cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
@@ -742,7 +766,8 @@ int favae_vq_search_tc(const void* xh, const void* eh, const float* xn, const fl
 
   p.mc = pl.mc;
   { const char* e = getenv("FAVAE_VQ_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
-  static bool configured = false;
+  static PerDevice<bool> configured_dev;
+  bool& configured = configured_dev.here();
   if (!configured) {
     FAVAE_CUDA_OK(cudaFuncSetAttribute(tc::vq_search_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)tc::SMEM_BYTES));

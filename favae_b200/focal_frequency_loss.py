@@ -40,59 +40,71 @@ def expected_upstream_scale(scale):
         _tls.scale = prev
 
 
+def _run_ffl(pred, target, loss_weight, alpha, log_matrix, batch_matrix, mean_count, gscale, need_p, need_t):
+    """One favae_ffl_forward call (two for batch_matrix): returns (loss (1,), grad_pred, grad_target).
+    ``target`` None: ``pred`` is already the difference map and grad_pred is dL/d(difference)."""
+    maps = pred.numel() // (pred.shape[-1] * pred.shape[-2])
+    h, w = pred.shape[-2], pred.shape[-1]
+    gp = torch.empty_like(pred) if need_p else None
+    gt = torch.empty_like(target) if need_t else None
+    dev = pred.device
+    map_loss = torch.empty((max(maps, 1),), device=dev, dtype=torch.float32)
+    st = _lib.stream()
+    if batch_matrix:
+        map_max = torch.empty((max(maps, 1),), device=dev, dtype=torch.float32)
+        _lib.call('favae_ffl_forward', _lib.ptr(pred), _lib.ptr(target), maps, h, w, alpha,
+                  int(log_matrix), 0.0, _lib.ptr(map_loss), None, None, _lib.ptr(map_max), None, st)
+        gmax = map_max[:maps].amax().reshape(1) if maps else torch.ones(1, device=dev)
+        _lib.call('favae_ffl_forward', _lib.ptr(pred), _lib.ptr(target), maps, h, w, alpha,
+                  int(log_matrix), gscale, _lib.ptr(map_loss), _lib.ptr(gp), _lib.ptr(gt), None,
+                  _lib.ptr(gmax), st)
+    else:
+        _lib.call('favae_ffl_forward', _lib.ptr(pred), _lib.ptr(target), maps, h, w, alpha,
+                  int(log_matrix), gscale, _lib.ptr(map_loss), _lib.ptr(gp), _lib.ptr(gt), None,
+                  None, st)
+    loss = torch.empty((1,), device=dev, dtype=torch.float32)
+    _lib.call('favae_sum_scaled', _lib.ptr(map_loss), maps, loss_weight / mean_count, _lib.ptr(loss), st)
+    return loss, gp, gt
+
+
 class _FFLFunction(torch.autograd.Function):
+    """The forward kernel already writes the gradients (scaled by the announced upstream factor), so
+    the first backward is a device-side "multiply by go / announced" that exits without touching
+    memory when that ratio is 1.  The buffers are handed to autograd once; a second backward through
+    the same graph (retain_graph) recomputes them from the saved inputs instead of un-scaling."""
 
     @staticmethod
     def forward(ctx, pred, target, loss_weight, alpha, log_matrix, batch_matrix, mean_count, grad_mode):
-        maps = pred.numel() // (pred.shape[-1] * pred.shape[-2])
-        h, w = pred.shape[-2], pred.shape[-1]
         need_p = grad_mode and ctx.needs_input_grad[0]
         need_t = grad_mode and ctx.needs_input_grad[1]
-        gp = torch.empty_like(pred) if need_p else None
-        gt = torch.empty_like(target) if need_t else None
-        dev = pred.device
-        map_loss = torch.empty((max(maps, 1),), device=dev, dtype=torch.float32)
         expected = getattr(_tls, 'scale', 1.0)
-        gscale = 2.0 * loss_weight / mean_count * expected
-        st = _lib.stream()
-        if batch_matrix:
-            map_max = torch.empty((max(maps, 1),), device=dev, dtype=torch.float32)
-            _lib.call('favae_ffl_forward', _lib.ptr(pred), _lib.ptr(target), maps, h, w, alpha,
-                      int(log_matrix), 0.0, _lib.ptr(map_loss), None, None, _lib.ptr(map_max), None, st)
-            gmax = map_max[:maps].amax().reshape(1) if maps else torch.ones(1, device=dev)
-            _lib.call('favae_ffl_forward', _lib.ptr(pred), _lib.ptr(target), maps, h, w, alpha,
-                      int(log_matrix), gscale, _lib.ptr(map_loss), _lib.ptr(gp), _lib.ptr(gt), None,
-                      _lib.ptr(gmax), st)
-        else:
-            _lib.call('favae_ffl_forward', _lib.ptr(pred), _lib.ptr(target), maps, h, w, alpha,
-                      int(log_matrix), gscale, _lib.ptr(map_loss), _lib.ptr(gp), _lib.ptr(gt), None,
-                      None, st)
-        loss = torch.empty((1,), device=dev, dtype=torch.float32)
-        _lib.call('favae_sum_scaled', _lib.ptr(map_loss), maps, loss_weight / mean_count, _lib.ptr(loss), st)
-        ctx.gp, ctx.gt = gp, gt
-        ctx.prev_scale = None
+        ctx.cfg = (loss_weight, alpha, log_matrix, batch_matrix, mean_count,
+                   2.0 * loss_weight / mean_count * expected, need_p, need_t)
+        with _lib.on_device_of(pred, target):
+            loss, gp, gt = _run_ffl(pred, target, *ctx.cfg)
+        if need_p or need_t:
+            ctx.save_for_backward(pred, target)
+        ctx.grads = (gp, gt)
         ctx.expected = expected
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, go):
-        gp, gt = ctx.gp, ctx.gt
-        if gp is None and gt is None:
+        if ctx.cfg[6] is False and ctx.cfg[7] is False:
             return (None,) * 8
-        go = go.detach().to(torch.float32).reshape(1).contiguous()
-        if ctx.expected != 1.0:
-            go = go / ctx.expected           # exactly 1.0 when the announced scale was applied
-        if ctx.prev_scale is not None:
-            # second backward through the same graph: undo the previous scale, work on copies
-            s = go / ctx.prev_scale
-            gp = gp.clone() if gp is not None else None
-            gt = gt.clone() if gt is not None else None
-        else:
-            s = go
-        ctx.prev_scale = go.clone() if ctx.prev_scale is None else ctx.prev_scale
-        a, b = (gp, gt) if gp is not None else (gt, None)
-        # grads were written by the forward kernel; this is a no-op unless go != 1
-        _lib.call('favae_scale_inplace', _lib.ptr(a), _lib.ptr(b), a.numel(), _lib.ptr(s), _lib.stream())
+        pred, target = ctx.saved_tensors
+        with _lib.on_device_of(pred, target):
+            if ctx.grads is None:                # re-entry: the first backward consumed the buffers
+                _, gp, gt = _run_ffl(pred, target, *ctx.cfg)
+            else:
+                gp, gt = ctx.grads
+            ctx.grads = None
+            s = go.detach().to(torch.float32).reshape(1)
+            if ctx.expected != 1.0:
+                s = s / ctx.expected             # exactly 1.0 when the announced scale was applied
+            s = s.contiguous()
+            a, b = (gp, gt) if gp is not None else (gt, None)
+            _lib.call('favae_scale_inplace', _lib.ptr(a), _lib.ptr(b), a.numel(), _lib.ptr(s), _lib.stream())
         return gp, gt, None, None, None, None, None, None
 
 
@@ -127,6 +139,11 @@ class FocalFrequencyLoss(nn.Module):
     def forward(self, pred, target, matrix=None, **kwargs):
         if matrix is not None:
             raise NotImplementedError('favae_b200: a predefined spectrum weight matrix is not supported')
+        from .gaussian_blur import LazyBlur
+        if isinstance(pred, LazyBlur):
+            pred = pred.materialize()
+        if isinstance(target, LazyBlur):
+            target = target.materialize()
         _lib.require_cuda(pred, target)
         if pred.shape != target.shape or pred.dim() != 4:
             raise RuntimeError(f'expected two (N,C,H,W) tensors of equal shape, got {tuple(pred.shape)} '

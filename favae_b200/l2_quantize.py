@@ -16,9 +16,20 @@ Everything on the hot path runs in hand-written sm_100a kernels behind the C ABI
   autograd backward            -> favae_vq_backward
 
 The two all-reduces of the reference (:419, :427) become ONE all-reduce of the flat
-``[bins | embed_sum]`` buffer.  There is no CPU path: CPU tensors raise.
+``[bins | embed_sum]`` buffer, issued on a side stream; the EMA update that consumes it is
+deferred to the next touch of the codebook (the next quantizer call, ``state_dict()``, any
+attribute access to ``embed`` / ``cluster_size``), so the collective overlaps whatever the
+training step does in between (the spectrum losses) instead of stalling the compute stream.
+The forward of a call only ever uses the pre-update codebook (reference :415 gathers before
+:421-438 update), so nothing observable changes.  There is no CPU path: CPU tensors raise.
+
+Environment switches: ``FAVAE_VQ_SEARCH=auto|tc|exact`` (search kernel),
+``FAVAE_VQ_DETERMINISTIC=1`` (bit-reproducible code statistics), ``FAVAE_VQ_CACHE=0`` (re-normalise
+the codebook on every call instead of reusing the rows the EMA kernel emitted).
 """
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.nn.functional as F
@@ -58,8 +69,26 @@ def orthogonal_loss_fn(t):
 
 
 def _search_mode():
-    import os
     return os.environ.get('FAVAE_VQ_SEARCH', 'auto')
+
+
+def _deterministic():
+    return os.environ.get('FAVAE_VQ_DETERMINISTIC', '0') not in ('', '0')
+
+
+def _cache_enabled():
+    return os.environ.get('FAVAE_VQ_CACHE', '1') not in ('', '0')
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One extra stream per device for the statistics all-reduce."""
+    key = torch.device(device).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+    return _SIDE_STREAMS[key]
 
 
 class _QuantizeFunction(torch.autograd.Function):
@@ -79,8 +108,9 @@ class _QuantizeFunction(torch.autograd.Function):
         gx = torch.empty_like(x)
         g_out = g_out.contiguous() if g_out is not None else None
         g_loss = g_loss.contiguous() if g_loss is not None else None
-        _lib.call('favae_vq_backward', _lib.ptr(x), _lib.ptr(out), _lib.ptr(g_out), _lib.ptr(g_loss),
-                  x.numel(), 2.0, _lib.ptr(gx), _lib.stream())
+        with _lib.on_device_of(x, g_out, g_loss):
+            _lib.call('favae_vq_backward', _lib.ptr(x), _lib.ptr(out), _lib.ptr(g_out), _lib.ptr(g_loss),
+                      x.numel(), 2.0, _lib.ptr(gx), _lib.stream())
         return gx, None, None, None, None
 
 
@@ -129,45 +159,160 @@ class _CodebookBase(nn.Module):
         else:
             self.register_buffer('embed', embed)
 
+    # -- deferred EMA ---------------------------------------------------------------------
+    _LAZY_NAMES = frozenset(('embed', 'cluster_size', 'embed_avg'))
+
+    def __getattr__(self, name):
+        # buffers / parameters live in _buffers / _parameters, so nn.Module resolves them here: a
+        # pending EMA update (see _after_stats) is applied before anybody can look at the codebook
+        if name in _CodebookBase._LAZY_NAMES and self.__dict__.get('_pending') is not None:
+            self._flush()
+        return super().__getattr__(name)
+
+    def _raw(self, name):
+        """Buffer / parameter without triggering the flush."""
+        t = self._buffers.get(name)
+        return t if t is not None else self._parameters[name]
+
+    def _flush(self):
+        """Apply the EMA update whose statistics were all-reduced on the side stream."""
+        pending = self.__dict__.get('_pending')
+        if pending is None:
+            return
+        self.__dict__['_pending'] = None
+        stats, en, eh, done = pending
+        with torch.cuda.device(stats.device):
+            torch.cuda.current_stream(stats.device).wait_event(done)
+            self._ema_update(en, eh, stats)
+
+    def _save_to_state_dict(self, *args, **kwargs):
+        self._flush()
+        return super()._save_to_state_dict(*args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._flush()
+        self.__dict__['_prep'] = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, *args, **kwargs):
+        self._flush()
+        self.__dict__['_prep'] = None
+        self.__dict__['_scratch'] = {}
+        return super()._apply(*args, **kwargs)
+
+    def __getstate__(self):
+        # pickling / deepcopy: finish the pending update, leave scratch, events and caches behind
+        self._flush()
+        state = self.__dict__.copy()
+        for key in ('_pending', '_prep', '_scratch'):
+            state.pop(key, None)
+        return state
+
+    def invalidate_cache(self):
+        """Forget the cached normalised codebook rows.  Needed only after writing to ``embed`` through
+        ``.data`` (which bypasses the tensor version counter that every other in-place write bumps)."""
+        self._flush()
+        self.__dict__['_prep'] = None
+
+    def _after_stats(self, en, eh, stats):
+        """Statistics of this call are ready on the current stream: all-reduce + EMA."""
+        import torch.distributed as dist
+        if self.use_ddp and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 \
+                and stats.is_cuda and self.threshold_ema_dead_code == 0:
+            # one all-reduce of [bins | embed_sum] (reference: two blocking ones, :419/:427 and :291/:295),
+            # on a side stream; the EMA waits for it at the next touch of the codebook (_flush)
+            side = _side_stream(stats.device)
+            side.wait_stream(torch.cuda.current_stream(stats.device))
+            with torch.cuda.stream(side):
+                _dist.all_reduce_stats(stats)
+                done = torch.cuda.Event()
+                done.record(side)
+            self.__dict__['_pending'] = (stats, en, eh, done)
+            return
+        if self.use_ddp:
+            _dist.all_reduce_stats(stats)      # raises like the reference without a process group
+        self._ema_update(en, eh, stats)
+
     # -- kernels --------------------------------------------------------------------------
-    def _prepare(self, x, n, hw, normalize, half):
+    def _buf(self, name, shape, dtype, device):
+        """Per-shape scratch reused from call to call (workspaces, keys, statistics): stream-ordered
+        reuse on the calling stream, never handed to the caller."""
+        sc = self.__dict__.setdefault('_scratch', {})
+        key = (name, tuple(shape), dtype, device)
+        t = sc.get(key)
+        if t is None:
+            if len(sc) > 64:
+                sc.clear()
+            t = sc[key] = torch.empty(shape, device=device, dtype=dtype)
+        return t
+
+    def _prepare(self, x, n, hw, normalize, half, out=None):
         d = self.dim
-        xn = torch.empty((n, d), device=x.device, dtype=torch.float32)
-        xh = torch.empty((n, d), device=x.device, dtype=torch.float16) if half else None
+        xn, xh = out if out is not None else (None, None)
+        if xn is None:
+            xn = torch.empty((n, d), device=x.device, dtype=torch.float32)
+        if half and xh is None:
+            xh = torch.empty((n, d), device=x.device, dtype=torch.float16)
         _lib.call('favae_vq_prepare_rows', _lib.ptr(x), n, d, hw, int(normalize), _lib.ptr(xn),
-                  _lib.ptr(xh), None, _lib.stream())
-        return xn, xh
+                  _lib.ptr(xh) if half else None, None, _lib.stream())
+        return xn, (xh if half else None)
+
+    def _prepared_codebook(self, use_tc):
+        """(en, eh) = l2norm(embed) in fp32 and 16x that in fp16.  The reference re-normalises the
+        whole codebook on every call (:408); here the EMA kernel emits the rows of the updated codebook
+        and they are reused as long as ``embed`` has not been written by anybody else (tensor version
+        counter + address)."""
+        embed_t = self._raw('embed')
+        embed = embed_t.detach()[0]
+        key = (embed_t.data_ptr(), embed_t._version, embed_t.device)
+        prep = self.__dict__.get('_prep')
+        if prep is not None and prep['key'] == key and _cache_enabled() and (prep['eh'] is not None or not use_tc):
+            return prep['en'], prep['eh']
+        k = self.codebook_size
+        out = (prep['en'], prep['eh']) if prep is not None and prep['en'].device == embed.device else None
+        en, eh = self._prepare(embed, k, 1, True, use_tc, out)
+        self.__dict__['_prep'] = {'key': key, 'en': en, 'eh': eh}
+        return en, eh
 
     def _search_rows(self, xn, xh, codes, n):
-        """Nearest code of every prepared latent row against ``codes`` (K, D).  Returns (idx, en)."""
-        k, d, dev = codes.shape[0], self.dim, xn.device
+        """Nearest code of every prepared latent row against ``codes`` (K, D), or against the module's
+        own codebook when ``codes`` is None.  Returns (idx, en, eh)."""
+        d, dev = self.dim, xn.device
         idx = torch.empty((n,), device=dev, dtype=torch.int64)
-        keys = torch.empty((n,), device=dev, dtype=torch.int64)
+        keys = self._buf('keys', (n,), torch.int64, dev)
+        eh = None
         if self.cosine:
             use_tc = xh is not None
-            en, eh = self._prepare(codes, k, 1, True, use_tc)
+            if codes is None:
+                en, eh = self._prepared_codebook(use_tc)
+            else:
+                en, eh = self._prepare(codes, codes.shape[0], 1, True, use_tc)
+            k = en.shape[0]
             if use_tc:
                 ws_bytes = _lib.load().favae_vq_search_tc_workspace_bytes(n, k, d)
-                ws = torch.empty((ws_bytes,), device=dev, dtype=torch.uint8)
+                ws = self._buf('ws', (ws_bytes,), torch.uint8, dev)
                 _lib.call('favae_vq_search_tc', _lib.ptr(xh), _lib.ptr(eh), _lib.ptr(xn), _lib.ptr(en),
                           n, k, d, _lib.ptr(ws), ws_bytes, _lib.ptr(keys), _lib.ptr(idx), _lib.stream())
             else:
                 _lib.call('favae_vq_search_exact', _lib.ptr(xn), _lib.ptr(en), None, n, k, d, 0,
                           _lib.ptr(keys), _lib.ptr(idx), _lib.stream())
         else:
+            if codes is None:
+                codes = self._raw('embed').detach()[0]
+            k = codes.shape[0]
             esq = torch.empty((k,), device=dev, dtype=torch.float32)
             en = torch.empty((k, d), device=dev, dtype=torch.float32)
             _lib.call('favae_vq_prepare_rows', _lib.ptr(codes), k, d, 1, 0, _lib.ptr(en), None,
                       _lib.ptr(esq), _lib.stream())
             _lib.call('favae_vq_search_exact', _lib.ptr(xn), _lib.ptr(en), _lib.ptr(esq), n, k, d, 1,
                       _lib.ptr(keys), _lib.ptr(idx), _lib.stream())
-        return idx, en
+        return idx, en, eh
 
-    def _code_stats(self, rows, idx, n):
+    def _code_stats(self, rows, idx, n, out=None):
         k, d = self.codebook_size, self.dim
-        stats = torch.empty((k * (d + 1),), device=rows.device, dtype=torch.float32)
-        _lib.call('favae_vq_code_stats', _lib.ptr(rows), _lib.ptr(idx), n, k, d, _lib.ptr(stats),
-                  _lib.stream())
+        stats = out if out is not None else torch.empty((k * (d + 1),), device=rows.device, dtype=torch.float32)
+        _lib.call('favae_vq_code_stats', _lib.ptr(rows), _lib.ptr(idx), n, k, d, int(_deterministic()),
+                  _lib.ptr(stats), _lib.stream())
         return stats
 
     @torch.no_grad()
@@ -188,7 +333,7 @@ class _CodebookBase(nn.Module):
         means = rows[pick].contiguous()
         bins = torch.zeros(k, device=rows.device)
         for _ in range(self.kmeans_iters):
-            idx, _ = self._search_rows(rows, xh, means, n)
+            idx, _, _ = self._search_rows(rows, xh, means, n)
             stats = self._code_stats(rows, idx, n)
             bins, esum = _dist.unpack_stats(stats, k, d)
             zero = bins == 0
@@ -202,6 +347,7 @@ class _CodebookBase(nn.Module):
         self.cluster_size.data.copy_(bins[None])
         self.initted.data.fill_(1.0)
         self._init_done = True
+        self.__dict__['_prep'] = None            # written through .data: the version counter did not move
 
     @torch.no_grad()
     def _expire_codes(self, rows):
@@ -220,9 +366,11 @@ class _CodebookBase(nn.Module):
         else:
             pick = torch.randint(0, n, (num,), device=rows.device)
         self.embed.data[0][expired] = samples[pick]
+        self.__dict__['_prep'] = None            # written through .data: the version counter did not move
 
     def _search_and_gather(self, x, n, hw, straight_through, want_loss):
         k, d, dev = self.codebook_size, self.dim, x.device
+        self._flush()                            # a deferred EMA update of the previous call comes first
         mode = _search_mode()
         use_tc = (self.cosine and mode != 'exact' and n > 0
                   and _lib.load().favae_vq_search_tc_workspace_bytes(n, k, d) > 0)
@@ -230,31 +378,32 @@ class _CodebookBase(nn.Module):
             raise RuntimeError('favae_b200: FAVAE_VQ_SEARCH=tc but the tensor-core search does not '
                                f'support dim={d}, codebook_size={k}')
         # rows: l2-normalised latents (cosine) or the rearranged raw latents (Euclidean)
-        xn, xh = self._prepare(x, n, hw, self.cosine, use_tc)
+        xn, xh = self._prepare(x, n, hw, self.cosine, use_tc,
+                               (self._buf('xn', (n, d), torch.float32, dev),
+                                self._buf('xh', (n, d), torch.float16, dev) if use_tc else None))
         self._kmeans_init(xn, xh, n)
-        embed = self.embed.detach()[0]
+        embed = self._raw('embed').detach()[0]
         if not embed.is_contiguous():
             raise RuntimeError('favae_b200: codebook buffer must be contiguous')
-        idx, en = self._search_rows(xn, xh, embed, n)
+        if embed.device != dev:
+            raise RuntimeError(f'favae_b200: latents on {dev} but the codebook is on {embed.device}')
+        idx, en, eh = self._search_rows(xn, xh, None, n)
 
         out = torch.empty_like(x)
         loss_sum = torch.zeros((1,), device=dev, dtype=torch.float32)
         blocks = (n + 31) // 32 if hw == 1 else (n // hw) * ((hw + 31) // 32)
-        partials = torch.empty((max(blocks, 1),), device=dev, dtype=torch.float32) if want_loss else None
+        partials = self._buf('partials', (max(blocks, 1),), torch.float32, dev) if want_loss else None
         _lib.call('favae_vq_gather_st', _lib.ptr(x), _lib.ptr(embed), _lib.ptr(idx), n, k, d, hw,
                   int(straight_through), _lib.ptr(out), _lib.ptr(partials),
                   _lib.ptr(loss_sum) if want_loss else None, _lib.stream())
 
         if self.training:
-            stats = self._code_stats(xn, idx, n)
-            if self.use_ddp:
-                # one all-reduce of [bins | embed_sum] (reference: two, :419/:427 and :291/:295)
-                _dist.all_reduce_stats(stats)
-            self._ema_update(en, stats)
+            stats = self._code_stats(xn, idx, n, self._buf('stats', (k * (d + 1),), torch.float32, dev))
+            self._after_stats(en, eh, stats)
             self._expire_codes(xn)
         return out, idx, loss_sum
 
-    def _ema_update(self, en, stats):
+    def _ema_update(self, en, eh, stats):
         raise NotImplementedError
 
     # -- reference-compatible codebook call: x (..., d) -> (quantize, embed_ind) --------------
@@ -264,7 +413,8 @@ class _CodebookBase(nn.Module):
         x = x.float().contiguous()
         shape = x.shape
         n = x.numel() // self.dim
-        out, idx, _ = self._search_and_gather(x, n, 1, False, False)
+        with _lib.on_device_of(x, self._raw('embed')):
+            out, idx, _ = self._search_and_gather(x, n, 1, False, False)
         return out.view(shape), idx.view(shape[:-1])
 
 
@@ -272,20 +422,30 @@ class CosineSimCodebook(_CodebookBase):
     """l2_quantize.py:308-444."""
     cosine = True
 
-    def _ema_update(self, en, stats):
-        _lib.call('favae_vq_ema_update_cosine', _lib.ptr(self.embed.data), _lib.ptr(self.cluster_size),
+    def _ema_update(self, en, eh, stats):
+        # the kernel also emits l2norm(updated codebook) into en / eh (in place), which stay valid for
+        # the next search as long as nobody else writes embed (_prepared_codebook)
+        embed_t = self._raw('embed')
+        prep = self.__dict__.get('_prep')
+        keep = _cache_enabled() and prep is not None and prep['en'] is en
+        _lib.call('favae_vq_ema_update_cosine', _lib.ptr(embed_t), _lib.ptr(self._raw('cluster_size')),
                   _lib.ptr(en), _lib.ptr(stats), self.codebook_size, self.dim, float(self.decay),
+                  _lib.ptr(en) if keep else None, _lib.ptr(eh) if keep and eh is not None else None,
                   _lib.stream())
+        if keep:
+            prep['key'] = (embed_t.data_ptr(), embed_t._version, embed_t.device)
+            if eh is None:
+                prep['eh'] = None
 
 
 class EuclideanCodebook(_CodebookBase):
     """l2_quantize.py:183-306, including the quirk that ``embed_avg`` is never refreshed (:294-300)."""
     cosine = False
 
-    def _ema_update(self, en, stats):
+    def _ema_update(self, en, eh, stats):
         scratch = torch.empty((2,), device=stats.device, dtype=torch.float32)
-        _lib.call('favae_vq_ema_update_euclid', _lib.ptr(self.embed.data), _lib.ptr(self.cluster_size),
-                  _lib.ptr(self.embed_avg), _lib.ptr(stats), self.codebook_size, self.dim,
+        _lib.call('favae_vq_ema_update_euclid', _lib.ptr(self._raw('embed')), _lib.ptr(self._raw('cluster_size')),
+                  _lib.ptr(self._raw('embed_avg')), _lib.ptr(stats), self.codebook_size, self.dim,
                   float(self.decay), float(self.eps), _lib.ptr(scratch), _lib.stream())
 
 
@@ -348,12 +508,17 @@ class VectorQuantize(nn.Module):
         else:
             out = torch.empty((n, d), device=idx.device, dtype=torch.float32)
             hw = 1
-        _lib.call('favae_vq_gather_rows', _lib.ptr(embed), _lib.ptr(idx), n, k, d, hw, _lib.ptr(out),
-                  _lib.stream())
+        with _lib.on_device_of(embed, idx):
+            _lib.call('favae_vq_gather_rows', _lib.ptr(embed), _lib.ptr(idx), n, k, d, hw, _lib.ptr(out),
+                      _lib.stream())
         return out
 
     def forward(self, x):
         _lib.require_cuda(x)
+        with _lib.on_device_of(x, self._codebook._raw('embed')):
+            return self._forward(x)
+
+    def _forward(self, x):
         device = x.device
         need_transpose = not self.channel_last and not self.accept_image_fmap
         projected = not isinstance(self.project_in, nn.Identity)
@@ -392,13 +557,23 @@ class VectorQuantize(nn.Module):
             if want_loss:
                 loss = loss + loss_sum * (self.commitment_weight / x.numel())    # :560-561
             if self.orthogonal_reg_weight > 0:                                  # :563-577
+                # Reproduced as written in the reference, quirks included: the (1, K, D) codebook is
+                # indexed and measured along dim 0 (the head axis, size 1).  `num_codes` is therefore 1,
+                # orthogonal_reg_max_codes never subsamples and no randperm is drawn; and
+                # orthogonal_reg_active_codes_only indexes dim 0 with code ids, which is an index error
+                # for any id > 0 (a device-side assert in the reference; a clean IndexError here).
                 codebook = cb.embed
                 if self.orthogonal_reg_active_codes_only:
-                    codebook = codebook[:, torch.unique(idx)]
-                num_codes = codebook.shape[1]
+                    unique_code_ids = torch.unique(idx)
+                    if int(unique_code_ids.max()) >= codebook.shape[0]:
+                        raise IndexError(f'index {int(unique_code_ids.max())} is out of bounds for dimension 0 '
+                                         f'with size {codebook.shape[0]} (orthogonal_reg_active_codes_only '
+                                         'indexes the head axis of the codebook, l2_quantize.py:569)')
+                    codebook = codebook[unique_code_ids]
+                num_codes = codebook.shape[0]
                 if exists(self.orthogonal_reg_max_codes) and num_codes > self.orthogonal_reg_max_codes:
                     rand_ids = torch.randperm(num_codes, device=device)[:self.orthogonal_reg_max_codes]
-                    codebook = codebook[:, rand_ids]
+                    codebook = codebook[rand_ids]
                 loss = loss + orthogonal_loss_fn(codebook) * self.orthogonal_reg_weight
 
         if heads > 1:                        # '1 (b h) n d -> b n (h d)', '1 (b h) n -> b n h'  (:579-585)

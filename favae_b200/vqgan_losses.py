@@ -1,13 +1,18 @@
 """Drop-in replacement for ``/root/reference/losses/vqgan_losses.py`` (same three functions,
 same arguments, same ``(loss (1,), [per-level scalars])`` returns, same in-place reversal of
 the caller's ``de_feat`` list).  The reference evaluates every level twice (:25-26, :45-46);
-here each level is evaluated once and the same tensor is returned in the list."""
+here each level is evaluated once and the same tensor is returned in the list.
+
+When the feature lists hold pending blurs (``LazyBlur`` handles, which is what the patched
+``_gaussian_blur`` methods return), ``recon_ffl_features_loss`` runs every level as the fused
+blur -> difference -> spectrum-loss op of :mod:`favae_b200.spectrum_dsl`."""
 from __future__ import annotations
 
 import torch
 
 from .focal_frequency_loss import expected_upstream_scale
 from .gaussian_blur import gaussian_blur_reflect
+from .spectrum_dsl import dsl_level_loss, fusable
 
 __all__ = ['recon_ffl_loss', 'recon_ffl_features_loss', 'recon_sl_gaussian_features_loss']
 
@@ -23,7 +28,10 @@ def recon_ffl_features_loss(ffl, en_feat, de_feat, device):            # :18-30
     inv = torch.tensor(1.0) / len(en_feat)          # the float32 factor `loss / len` applies
     with expected_upstream_scale(float(inv)):
         for i in range(len(en_feat)):
-            level = ffl(de_feat[i], en_feat[i])
+            if fusable(ffl, de_feat[i], en_feat[i]):
+                level = dsl_level_loss(ffl, de_feat[i], en_feat[i])
+            else:
+                level = ffl(de_feat[i], en_feat[i])
             loss = loss + level
             losses.append(level)
     loss = loss * inv.to(loss.device)

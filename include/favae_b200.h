@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FAVAE_B200_ABI_VERSION 1
+#define FAVAE_B200_ABI_VERSION 2
 
 int favae_abi_version(void);
 const char* favae_last_error(void);
@@ -81,14 +81,22 @@ int favae_vq_gather_st(const float* x, const float* embed, const int64_t* idx, i
 /* Code usage statistics: bins = bincount(idx) (l2_quantize.py:412,418) and
  * embed_sum = scatter-add of xn rows by idx (:426, the reference's second dense GEMM).
  * stats = [bins (K) | embed_sum (K*D)] fp32, zeroed by this call: one flat buffer so that the
- * data-parallel exchange is a single all-reduce (reference: two, :419 and :427). */
+ * data-parallel exchange is a single all-reduce (reference: two, :419 and :427).
+ * deterministic == 0: scatter-add with fp32 atomics (arrival order, ~1e-7 run-to-run noise);
+ * deterministic != 0: one warp per code adds its members in ascending latent order --
+ * bit-reproducible (the reference's one-hot GEMM, :426, is deterministic too). */
 int favae_vq_code_stats(const float* xn, const int64_t* idx, int64_t n, int64_t k, int d,
-                        float* stats, void* stream);
+                        int deterministic, float* stats, void* stream);
 
 /* EMA codebook update, cosine codebook (l2_quantize.py:421-438). en = l2norm(embed) as
- * produced by favae_vq_prepare_rows on the pre-update codebook. */
+ * produced by favae_vq_prepare_rows on the pre-update codebook.
+ * en_next (K*D fp32, nullable, may alias en) and eh_next (K*D fp16, nullable) receive
+ * l2norm(updated embed) and 16x that in fp16 -- bit-identical to what favae_vq_prepare_rows
+ * would produce -- so the next search (l2_quantize.py:408, re-normalising the whole codebook
+ * every call) starts without a preparation pass. */
 int favae_vq_ema_update_cosine(float* embed, float* cluster_size, const float* en,
-                               const float* stats, int64_t k, int d, float decay, void* stream);
+                               const float* stats, int64_t k, int d, float decay,
+                               float* en_next, void* eh_next, void* stream);
 
 /* EMA update, Euclidean codebook (l2_quantize.py:292-300) including its quirk that
  * embed_avg is never refreshed. */
@@ -114,6 +122,9 @@ int favae_vq_gather_rows(const float* embed, const int64_t* idx, int64_t n, int6
  * their autograd backward.  map_loss[m] = sum_{u,v} w * |F(pred - target)|^2 (ortho FFT);
  * grad_pred / grad_target (nullable) receive +/- grad_scale * N^2 * Re ifft2(w . F) -- pass
  * grad_scale = 2 * loss_weight / numel.
+ * target == NULL: `pred` already holds the difference map pred - target (the fused DSL op,
+ * favae_blur_diff_forward); grad_target must then be NULL and grad_pred receives the single
+ * gradient map G = dL/d(difference) (8 instead of 16 bytes per element).
  * map_max (nullable) receives max_{u,v} f(|F|) per map; fmax_override (nullable, one device
  * scalar) replaces the per-map maximum in the weight (batch_matrix=True).
  * alpha == 1 without log weighting and grad_scale >= 0 (every call the reference makes) runs a
@@ -139,13 +150,28 @@ int favae_scale_inplace(float* a, float* b, int64_t n, const float* s, void* str
  * (losses/vqgan_losses.py:35). */
 int favae_blur_forward(const float* x, int64_t maps, int h, int w, int ksize, const float* sigma,
                        float* y, void* stream);
-/* gx = adjoint blur of gy;  gsigma[0] = d/dsigma <gy, blur(x)> (nullable; partials =
- * favae_blur_partials(maps,h,w) floats of scratch).  Diagnostics only: the environment variable
- * FAVAE_BLUR_SIGMA=split computes the two results with two kernels instead of the fused one. */
+/* gx = out_scale * adjoint blur of gy;  gsigma[0] = out_scale * d/dsigma <gy, blur(x)>
+ * (nullable; partials = favae_blur_partials(maps,h,w) floats of scratch).  out_scale != 1 (the
+ * fused DSL op passes -1 for the encoder side) needs favae_blur_fast_supported(h, w, ksize).
+ * Diagnostics only: the environment variable FAVAE_BLUR_SIGMA=split computes the two results
+ * with two kernels instead of the fused one. */
 int64_t favae_blur_partials(int64_t maps, int h, int w);
 int favae_blur_backward(const float* gy, const float* x, int64_t maps, int h, int w, int ksize,
-                        const float* sigma, float* gx, float* gsigma, float* partials,
-                        void* stream);
+                        const float* sigma, float out_scale, float* gx, float* gsigma,
+                        float* partials, void* stream);
+
+/* 1 when the streaming blur kernels take this shape: w a power of two in [8, 512],
+ * ksize in {3,5,9,11,15}, ksize/2 < min(h, w). */
+int favae_blur_fast_supported(int h, int w, int ksize);
+
+/* d = blur(dec, sigma_dec) - blur(enc, sigma_enc) in one pass (12 bytes per element): the
+ * blurred FCM feature pair of the DSL (models/vqgan_fcm.py:131-134; models/codec.py:284-309,
+ * 655-686, 978-999, 1105-1123) is consumed only by ffl(de_feat, en_feat)
+ * (losses/vqgan_losses.py:25), which depends on the difference alone, so the two blurred maps
+ * are never materialised.  Needs favae_blur_fast_supported and 16-byte aligned maps. */
+int favae_blur_diff_forward(const float* enc, const float* dec, int64_t maps, int h, int w,
+                            int ksize, const float* sigma_enc, const float* sigma_dec, float* d,
+                            void* stream);
 
 #ifdef __cplusplus
 }

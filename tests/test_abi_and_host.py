@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(raw, n), f'{n} declared in include/favae_b200.h but not exported'
         assert n in _lib.SIGNATURES, f'{n} has no ctypes signature'
-    assert lib.favae_abi_version() == 1
+    assert lib.favae_abi_version() == 2
     assert lib.favae_ffl_supported(256, 256) == 1 and lib.favae_ffl_supported(24, 24) == 0
 
 
