@@ -113,9 +113,36 @@ def on_device_of(*tensors):
     return torch.cuda.device(dev)
 
 
+_trace = None
+
+
+def start_trace(names):
+    """Measurement hook (bench.py): bracket every call of the named entry points with CUDA events on
+    the launching stream, so a kernel family can be timed inside a real step without the benchmark
+    re-implementing the call sequence."""
+    global _trace
+    _trace = {n: [] for n in names}
+
+
+def stop_trace():
+    """-> {name: [(milliseconds, args), ...]} (synchronises)."""
+    global _trace
+    tr, _trace = _trace, None
+    torch.cuda.synchronize()
+    return {n: [(a.elapsed_time(b), args) for a, b, args in v] for n, v in (tr or {}).items()}
+
+
 def call(name: str, *args):
     lib = load()
-    rc = getattr(lib, name)(*args)
+    tr = _trace
+    if tr is not None and name in tr:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = getattr(lib, name)(*args)
+        b.record()
+        tr[name].append((a, b, args))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f'{name} failed ({rc}): {lib.favae_last_error().decode()}')
 

@@ -80,6 +80,39 @@ def vq_case(l2q, name, *, K, D, B, h, w, cosine, steps, commit=1.0, dim=None, se
     print('wrote', name)
 
 
+def vq_big_case(l2q, name, *, K, D=256, B=1, h=8, w=8, seed=11, ortho=0.0):
+    """Production codebook shapes (K x 256) at small N.  The codebook is not stored (16 MB at
+    K = 16384): it is the module's own seeded initialisation, which the test regenerates with the same
+    torch CPU generator and checks against the recorded digest; of the updated codebook only the rows
+    of the codes that were hit (plus a few that were not) are kept."""
+    torch.manual_seed(seed)
+    vq = l2q.VectorQuantize(dim=D, codebook_size=K, accept_image_fmap=True, use_cosine_sim=True,
+                            commitment_weight=1.0, orthogonal_reg_weight=ortho,
+                            orthogonal_reg_max_codes=128 if ortho else None)
+    vq.train()
+    e0 = vq._codebook.embed.detach()[0].clone()
+    rec = {'K': K, 'D': D, 'seed': seed, 'ortho': ortho,
+           'embed0_sum': np.float64(e0.double().sum().item()), 'embed0_abs': np.float64(e0.double().abs().sum().item()),
+           'embed0_row7': _np(e0[7])}
+    g = torch.Generator().manual_seed(4321 + seed)
+    x = torch.randn(B, D, h, w, generator=g).requires_grad_(True)
+    gq = torch.randn(B, D, h, w, generator=g)
+    q, ind, loss = vq(x)
+    (q * gq).sum().add(loss.sum() * 0.7).backward()
+    e1 = vq._codebook.embed.detach()[0]
+    hit = torch.unique(ind)
+    rows = torch.cat([hit, torch.tensor([0, 1, K // 2, K - 1])]).unique()
+    rec.update(x=_np(x), gq=_np(gq), q=_np(q), ind=_np(ind), loss=_np(loss), gx=_np(x.grad),
+               rows=_np(rows), embed1_rows=_np(e1[rows]), cluster1_rows=_np(vq._codebook.cluster_size[0][rows]),
+               embed1_sum=np.float64(e1.double().sum().item()),
+               cluster1_sum=np.float64(vq._codebook.cluster_size.double().sum().item()))
+    if ortho:
+        ge = vq._codebook.embed.grad[0]
+        rec.update(gembed_rows=_np(ge[rows]), gembed_abs=np.float64(ge.double().abs().sum().item()))
+    np.savez_compressed(os.path.join(OUT, f'vq_{name}.npz'), **rec)
+    print('wrote', name, 'hit codes', hit.numel())
+
+
 def _ddp_worker(rank, world, port, K, D, B, h, w, q):
     import torch.distributed as dist
     warnings.filterwarnings('ignore')
@@ -181,6 +214,9 @@ def main():
     vq_case(l2q, 'cos_proj', K=128, D=32, B=2, h=8, w=8, cosine=True, steps=2, dim=3, seed=2)
     vq_case(l2q, 'euclid_small', K=64, D=32, B=2, h=4, w=4, cosine=False, steps=2, seed=3)
     vq_case(l2q, 'cos_heads2', K=64, D=32, B=2, h=4, w=4, cosine=True, steps=2, seed=4, heads=2)
+    vq_big_case(l2q, 'big_k1024', K=1024)
+    vq_big_case(l2q, 'big_k16384', K=16384, B=2, seed=12)
+    vq_big_case(l2q, 'big_ortho', K=1024, seed=13, ortho=10.0)
     vq_ddp_case('cos_ddp2')
     blur_cases(VQGANFCM)
     wrapper_cases(vl)

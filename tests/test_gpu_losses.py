@@ -12,6 +12,25 @@ from oracle import ffl_oracle as fo
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-4
+EPS32 = 2.0 ** -24
+
+
+def sigma_grad_reference(x, go, sigma, k):
+    """fp64 value of d<go, blur(x; sigma)>/dsigma = sum_i go_i u_i (u = d blur / d sigma, forward-mode
+    through the oracle) and sum_i |go_i u_i|.  The second number is the conditioning of the sum: an fp32
+    evaluation of it (4-9 roundings per product, tree summation) cannot be closer than a few eps32 of
+    it, whatever the algorithm -- with zero-mean random go the sum cancels to ~1/sqrt(N) of it."""
+    xd, god = x.double(), go.double()
+    sd = torch.as_tensor(sigma, dtype=torch.float64, device=xd.device)
+    _, u = torch.func.jvp(lambda s: bo.gaussian_blur_reflect(xd, s, k), (sd,), (torch.ones_like(sd),))
+    t = god * u
+    return float(t.sum()), float(t.abs().sum())
+
+
+def assert_sigma_grad(got, ref, sum_abs):
+    """north_star tolerance (1e-4 relative) plus the fp32 floor of the sum: 8 eps32 * sum |terms|
+    (measured: profiles/sigma_grad_error_r2.txt, worst observed 1.4 eps32 * sum |terms|)."""
+    assert abs(float(got) - ref) <= RTOL * abs(ref) + 8 * EPS32 * sum_abs, (float(got), ref, sum_abs)
 
 
 def _run(shape, seed=0, **kw):
@@ -120,7 +139,12 @@ def test_blur_matches_reference_fixture(golden_dir):
         torch.testing.assert_close(y.cpu(), torch.from_numpy(g[f'y{i}']), rtol=1e-4, atol=1e-6)
         (y * torch.from_numpy(g[f'go{i}']).cuda()).sum().backward()
         torch.testing.assert_close(x.grad.cpu(), torch.from_numpy(g[f'gx{i}']), rtol=1e-4, atol=1e-6)
-        assert float(sig.grad[1]) == pytest.approx(float(g[f'gsig{i}']), rel=2e-3, abs=1e-5)
+        # the fixture's sigma gradient is the reference's own float32 autograd result; the fp64 value of
+        # the same sum is the arbiter, and the reference has to be as close to it as we are held to be
+        ref, sum_abs = sigma_grad_reference(torch.from_numpy(g[f'x{i}']), torch.from_numpy(g[f'go{i}']),
+                                            float(g[f'sigma{i}']), int(g[f'k{i}']))
+        assert_sigma_grad(sig.grad[1], ref, sum_abs)
+        assert abs(float(g[f'gsig{i}']) - ref) <= 10 * RTOL * abs(ref) + 64 * EPS32 * sum_abs
         assert float(sig.grad[0]) == 0.0
 
 
@@ -142,7 +166,15 @@ def test_blur_vs_oracle(shape, k):
     (y * go.cuda()).sum().backward()
     assert (y.cpu().double() - yd).abs().max() <= RTOL * yd.abs().max()
     assert (xg.grad.cpu().double() - xd.grad).abs().max() <= RTOL * xd.grad.abs().max()
-    assert float(sg.grad) == pytest.approx(float(sd.grad), rel=1e-3, abs=1e-4)
+    ref, sum_abs = sigma_grad_reference(x, go, 3.0, k)
+    assert float(sd.grad) == pytest.approx(ref, rel=1e-9, abs=1e-12 * sum_abs)     # reverse == forward mode
+    assert_sigma_grad(sg.grad, ref, sum_abs)
+    # a well-conditioned sum (all terms of one sign) must meet the plain 1e-4
+    xp, gp = x.abs() + 1.0, go.abs() + 0.5
+    refp, sum_absp = sigma_grad_reference(xp, gp, 3.0, k)
+    xg2 = xp.cuda().requires_grad_(True); sg2 = torch.tensor(3.0, device='cuda', requires_grad=True)
+    (gaussian_blur_reflect(xg2, sg2, k) * gp.cuda()).sum().backward()
+    assert_sigma_grad(sg2.grad, refp, sum_absp)
 
 
 def test_wrappers_match_reference_fixture(golden_dir):
@@ -180,8 +212,15 @@ def test_dsl_gradients_reach_sigma_and_features():
     assert abs(loss.item() - ref.item()) <= RTOL * abs(ref.item())
     assert (eg.grad.cpu().double() - ed.grad).abs().max() <= RTOL * ed.grad.abs().max()
     assert (dg.grad.cpu().double() - dd.grad).abs().max() <= RTOL * dd.grad.abs().max()
-    assert float(s1.grad) == pytest.approx(float(t1.grad), rel=2e-3)
-    assert float(s2.grad) == pytest.approx(float(t2.grad), rel=2e-3)
+    # the upstream gradient of each blur is +-G, the spectrum-loss gradient (taken from the oracle)
+    pb = bo.gaussian_blur_reflect(dd.detach(), t2.detach(), 9).requires_grad_(True)
+    fo.focal_frequency_loss(pb, bo.gaussian_blur_reflect(ed.detach(), t1.detach(), 9), loss_weight=0.01).backward()
+    G = pb.grad
+    r1, a1 = sigma_grad_reference(e, -G, 3.0, 9)
+    r2, a2 = sigma_grad_reference(d, G, 2.0, 9)
+    assert r1 == pytest.approx(float(t1.grad), rel=1e-8) and r2 == pytest.approx(float(t2.grad), rel=1e-8)
+    assert_sigma_grad(s1.grad, r1, a1)
+    assert_sigma_grad(s2.grad, r2, a2)
 
 
 def test_f4_config_end_to_end_vs_oracle():
@@ -229,7 +268,9 @@ def test_f4_config_end_to_end_vs_oracle():
     np.testing.assert_allclose([float(v) for v in lst], [float(v) for v in lsto], rtol=RTOL)
     for a, b in zip(eg + dg, ed + dd):
         assert (a.grad.cpu() - b.grad).abs().max() <= 2e-4 * b.grad.abs().max()
-    np.testing.assert_allclose(sig.grad.cpu().numpy(), so.grad.numpy(), rtol=5e-3, atol=1e-7)
+    # (this oracle leg runs in float32 like the reference: its own sigma gradients carry float32 noise;
+    # the fp64-held sigma checks are test_dsl_gradients_reach_sigma_and_features / test_fused_dsl_*)
+    np.testing.assert_allclose(sig.grad.cpu().numpy(), so.grad.numpy(), rtol=1e-3, atol=1e-7)
     # quantizer: indices vs oracle on the projected latents (near-ties allowed by score gap)
     idx_o, xn_o, en_o = vo.cosine_search(flat, embed0)
     bad = (ind.reshape(-1).cpu() != idx_o).nonzero().flatten()
@@ -305,4 +346,206 @@ def test_full_size_properties_level0():
         yp = gaussian_blur_reflect(x, torch.tensor(3.0 + h, device='cuda'), 9)
         ym = gaussian_blur_reflect(x, torch.tensor(3.0 - h, device='cuda'), 9)
         fd = float(((yp.double() - ym.double()) * go.double()).sum()) / (2 * h)
-    assert float(sig.grad) == pytest.approx(fd, rel=5e-3, abs=1.0)
+    # central difference of an fp32 blur: truncation h^2 and rounding eps/h bound what this can show
+    assert float(sig.grad) == pytest.approx(fd, rel=2e-3, abs=1.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused DSL level: blur -> difference -> spectrum loss -> adjoint + sigma gradients, no blurred maps
+# ------------------------------------------------------------------------------------------------
+def _dsl_reference(e, d, s_e, s_d, k, lw):
+    ed, dd = e.double().requires_grad_(True), d.double().requires_grad_(True)
+    te = torch.tensor(s_e, dtype=torch.float64, requires_grad=True)
+    td = torch.tensor(s_d, dtype=torch.float64, requires_grad=True)
+    pb = bo.gaussian_blur_reflect(dd, td, k)
+    pb.retain_grad()
+    ref = fo.focal_frequency_loss(pb, bo.gaussian_blur_reflect(ed, te, k), loss_weight=lw)
+    ref.backward()
+    G = pb.grad
+    return ref, ed.grad, dd.grad, sigma_grad_reference(e, -G, s_e, k), sigma_grad_reference(d, G, s_d, k), (te, td)
+
+
+@pytest.mark.parametrize('shape,k', [((1, 4, 64, 64), 9), ((2, 3, 16, 16), 9), ((1, 2, 256, 256), 9),
+                                     ((1, 3, 128, 128), 5), ((3, 2, 32, 32), 3), ((1, 5, 8, 8), 3),
+                                     ((1, 1, 512, 512), 11)])
+def test_fused_dsl_level_vs_oracle(shape, k):
+    from favae_b200 import FocalFrequencyLoss, LazyBlur, lazy_gaussian_blur
+    from favae_b200 import spectrum_dsl
+    g = torch.Generator().manual_seed(31 + k)
+    e = torch.randn(*shape, generator=g); d = torch.randn(*shape, generator=g)
+    eg, dg = e.cuda().requires_grad_(True), d.cuda().requires_grad_(True)
+    s_e = torch.tensor(2.5, device='cuda', requires_grad=True); s_d = torch.tensor(3.5, device='cuda', requires_grad=True)
+    ffl = FocalFrequencyLoss(loss_weight=0.01)
+    pe, pd_ = lazy_gaussian_blur(eg, s_e, k), lazy_gaussian_blur(dg, s_d, k)
+    assert isinstance(pe, LazyBlur) and spectrum_dsl.fusable(ffl, pd_, pe)
+    loss = spectrum_dsl.dsl_level_loss(ffl, pd_, pe)
+    assert pe._lazy_value is None and pd_._lazy_value is None        # nothing was materialised
+    (loss * 1.0).backward()
+    ref, ge, gd, (r_e, a_e), (r_d, a_d), (te, td) = _dsl_reference(e, d, 2.5, 3.5, k, 0.01)
+    assert r_e == pytest.approx(float(te.grad), rel=1e-8) and r_d == pytest.approx(float(td.grad), rel=1e-8)
+    assert abs(loss.item() - ref.item()) <= RTOL * abs(ref.item())
+    assert (eg.grad.cpu().double() - ge).abs().max() <= RTOL * ge.abs().max()
+    assert (dg.grad.cpu().double() - gd).abs().max() <= RTOL * gd.abs().max()
+    assert_sigma_grad(s_e.grad, r_e, a_e)
+    assert_sigma_grad(s_d.grad, r_d, a_d)
+
+
+def test_fused_dsl_equals_unfused_path_and_reenters():
+    """Same inputs through the fused op and through blur, blur, spectrum loss on materialised maps;
+    upstream scaling, a second backward (retain_graph) and no_grad."""
+    from favae_b200 import FocalFrequencyLoss, gaussian_blur_reflect, lazy_gaussian_blur
+    from favae_b200 import vqgan_losses as vl
+    g = torch.Generator().manual_seed(77)
+    shapes = [(2, 8, 256, 256), (2, 16, 16, 16), (2, 16, 16, 16), (2, 8, 16, 16)]
+    en = [torch.randn(*s_, generator=g).cuda() for s_ in shapes]
+    de = [torch.randn(*s_, generator=g).cuda() for s_ in reversed(shapes)]
+    dsl = FocalFrequencyLoss(loss_weight=0.01)
+    outs = []
+    for lazy in (True, False):
+        blur = lazy_gaussian_blur if lazy else gaussian_blur_reflect
+        e = [t.clone().requires_grad_(True) for t in en]; d = [t.clone().requires_grad_(True) for t in de]
+        se = torch.full((4,), 3.0, device='cuda', requires_grad=True); sd = torch.full((4,), 2.0, device='cuda', requires_grad=True)
+        eb = [blur(e[i], se[i], 9) for i in range(4)]; db = [blur(d[i], sd[i], 9) for i in range(4)]
+        db_list = list(db)
+        loss, lst = vl.recon_ffl_features_loss(dsl, eb, db_list, 'cuda')
+        assert db_list[0] is db[3] and loss.shape == (1,) and len(lst) == 4
+        if lazy:
+            assert all(t._lazy_value is None for t in eb + db)
+        (loss.sum() * 0.37).backward(retain_graph=True)
+        first = [t.grad.clone() for t in e + d] + [se.grad.clone(), sd.grad.clone()]
+        for t in e + d + [se, sd]:
+            t.grad = None
+        (loss.sum() * 0.37).backward()              # re-entry must give the same gradients again
+        second = [t.grad.clone() for t in e + d] + [se.grad.clone(), sd.grad.clone()]
+        for a, b in zip(first, second):
+            torch.testing.assert_close(a, b, rtol=1e-6, atol=0)
+        outs.append((loss.detach(), [v.detach() for v in lst], first))
+    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=1e-5, atol=0)
+    for a, b in zip(outs[0][1], outs[1][1]):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=0)
+    for a, b in zip(outs[0][2][:8], outs[1][2][:8]):
+        assert (a - b).abs().max() <= 2e-5 * b.abs().max()
+    for a, b in zip(outs[0][2][8:], outs[1][2][8:]):     # sigma gradients, both fp32
+        torch.testing.assert_close(a, b, rtol=2e-3, atol=1e-7)
+    with torch.no_grad():
+        v, _ = vl.recon_ffl_features_loss(dsl, [lazy_gaussian_blur(t, 3.0, 9) for t in en],
+                                          [lazy_gaussian_blur(t, 2.0, 9) for t in de], 'cuda')
+    assert not v.requires_grad
+    torch.testing.assert_close(v, outs[1][0], rtol=1e-5, atol=0)
+
+
+def test_lazy_blur_materialises_transparently():
+    """Anything other than the fused loss that touches a deferred blur gets the blurred tensor."""
+    from favae_b200 import FocalFrequencyLoss, gaussian_blur_reflect, lazy_gaussian_blur
+    from favae_b200 import vqgan_losses as vl
+    x = torch.randn(2, 3, 32, 32, device='cuda', requires_grad=True)
+    s = torch.tensor(1.7, device='cuda', requires_grad=True)
+    z = lazy_gaussian_blur(x, s, 5)
+    y = gaussian_blur_reflect(x, s, 5)
+    assert z.shape == y.shape and z.device == y.device and z.dtype == y.dtype and z.requires_grad
+    assert torch.equal(z + 0, y) and torch.equal(torch.sum(z, dim=1), y.sum(1)) and torch.equal(z.float(), y)
+    assert type(z * 2) is torch.Tensor
+    (z * y).sum().backward()
+    assert x.grad is not None and s.grad is not None
+    # mixed pair (one handle, one tensor) and the fixed-sigma SL wrapper both work on handles
+    ffl = FocalFrequencyLoss(loss_weight=0.5)
+    a = float(ffl(lazy_gaussian_blur(x, s, 5), y.detach() * 0.5))
+    b = float(ffl(y, y.detach() * 0.5))
+    assert a == b
+    en = [lazy_gaussian_blur(x.detach(), 2.0, 5)] * 4
+    l1, _ = vl.recon_sl_gaussian_features_loss(ffl, 5, 3, list(en), list(en), 'cuda')
+    assert float(l1) == 0.0
+    x2 = x.detach().clone()
+    h = lazy_gaussian_blur(x2, 2.0, 5)
+    x2.add_(1.0)
+    with pytest.raises(RuntimeError):
+        h + 0
+
+
+def _ffl_cufft(p, t, lw):
+    """Independent GPU restatement with cuFFT (SURVEY.md 8c "second opinion"): rfft2 of the difference,
+    Hermitian multiplicities for the half spectrum, per-map max, autograd for the gradient."""
+    d = p - t
+    F_ = torch.fft.rfft2(d, norm='ortho')
+    m2 = F_.real ** 2 + F_.imag ** 2
+    w = m2.sqrt()
+    wmax = w.amax(dim=(-2, -1), keepdim=True)
+    w = torch.nan_to_num(w / wmax, nan=0.0).clamp(0.0, 1.0).detach()
+    W = p.shape[-1]
+    mult = torch.full((W // 2 + 1,), 2.0, device=p.device)
+    mult[0] = 1.0; mult[-1] = 1.0
+    return (w * m2 * mult).sum() * (lw / p.numel())
+
+
+def test_full_size_level0_against_cufft_and_conv2d():
+    """Batch 32 level-0 size (4096 maps of 256^2 per tensor): the spectrum loss and both gradients
+    against a cuFFT restatement, the blur forward / adjoint / sigma gradient against F.conv2d autograd,
+    and the fused DSL level against the composition of the two -- all at the full BASELINE size."""
+    from favae_b200 import FocalFrequencyLoss, gaussian_blur_reflect, lazy_gaussian_blur
+    from favae_b200 import spectrum_dsl
+    import torch.nn.functional as F
+    if torch.cuda.mem_get_info()[0] < 40 << 30:
+        pytest.skip('needs 40 GB of free device memory')
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        shape = (32, 128, 256, 256)
+        g = torch.Generator(device='cuda').manual_seed(5)
+        p = torch.randn(shape, device='cuda', generator=g).requires_grad_(True)
+        t = torch.randn(shape, device='cuda', generator=g).requires_grad_(True)
+        ffl = FocalFrequencyLoss(loss_weight=0.01)
+        loss = ffl(p, t)
+        loss.backward()
+        ref_loss = 0.0
+        worst = 0.0
+        gmax = 0.0
+        for b0 in range(0, 32, 4):                      # cuFFT leg in chunks of 4 images
+            pc = p.detach()[b0:b0 + 4].clone().requires_grad_(True)
+            tc = t.detach()[b0:b0 + 4].clone().requires_grad_(True)
+            l = _ffl_cufft(pc, tc, 0.01) * (4 / 32)     # mean over the whole batch
+            l.backward()
+            ref_loss += float(l)
+            worst = max(worst, float((p.grad[b0:b0 + 4] - pc.grad).abs().max()),
+                        float((t.grad[b0:b0 + 4] - tc.grad).abs().max()))
+            gmax = max(gmax, float(pc.grad.abs().max()))
+        assert float(loss) == pytest.approx(ref_loss, rel=RTOL)
+        assert worst <= RTOL * gmax
+        # blur against reflect-pad + depthwise conv2d (the reference's own ops, vqgan_fcm.py:35-41)
+        def conv_blur(x, sigma, k):
+            half = (k - 1) * 0.5
+            xs = torch.linspace(-half, half, steps=k, device=x.device)
+            pdf = torch.exp(-0.5 * (xs / sigma) ** 2)
+            k1 = pdf / pdf.sum()
+            k2 = (k1[:, None] @ k1[None, :]).repeat(x.shape[1], 1, 1, 1)
+            return F.conv2d(F.pad(x, [k // 2] * 4, mode='reflect'), k2, groups=x.shape[1])
+        x = p.detach()[:8]
+        go = t.detach()[:8]
+        xs = x.clone().requires_grad_(True); sig = torch.tensor(3.0, device='cuda', requires_grad=True)
+        y = gaussian_blur_reflect(xs, sig, 9)
+        (y * go).sum().backward()
+        xr = x.clone().requires_grad_(True); sr = torch.tensor(3.0, device='cuda', requires_grad=True)
+        yr = conv_blur(xr, sr, 9)
+        (yr * go).sum().backward()
+        assert (y - yr).abs().max() <= RTOL * yr.abs().max()
+        assert (xs.grad - xr.grad).abs().max() <= RTOL * xr.grad.abs().max()
+        # both sigma gradients are fp32 sums over 67 M cancelling terms: compare through the conditioning
+        sum_abs = float((go.double() * 0.06 * x.double().abs()).sum())      # |u| <~ 0.06 |x| scale, see sigma_grad_reference
+        assert abs(float(sig.grad) - float(sr.grad)) <= RTOL * abs(float(sr.grad)) + 16 * EPS32 * sum_abs
+        del xs, xr, y, yr
+        # fused DSL level at full size against its own unfused composition
+        p.grad = None; t.grad = None
+        s_e = torch.tensor(3.0, device='cuda', requires_grad=True); s_d = torch.tensor(2.5, device='cuda', requires_grad=True)
+        dsl = FocalFrequencyLoss(loss_weight=0.01)
+        lf = spectrum_dsl.dsl_level_loss(dsl, lazy_gaussian_blur(p, s_d, 9), lazy_gaussian_blur(t, s_e, 9))
+        lf.backward()
+        gp_f, gt_f, gse_f, gsd_f = p.grad.clone(), t.grad.clone(), float(s_e.grad), float(s_d.grad)
+        p.grad = None; t.grad = None; s_e.grad = None; s_d.grad = None
+        lu = dsl(gaussian_blur_reflect(p, s_d, 9), gaussian_blur_reflect(t, s_e, 9))
+        lu.backward()
+        assert float(lf) == pytest.approx(float(lu), rel=1e-5)
+        assert (gp_f - p.grad).abs().max() <= 2e-5 * p.grad.abs().max()
+        assert (gt_f - t.grad).abs().max() <= 2e-5 * t.grad.abs().max()
+        assert gse_f == pytest.approx(float(s_e.grad), rel=2e-3, abs=1e-9)
+        assert gsd_f == pytest.approx(float(s_d.grad), rel=2e-3, abs=1e-9)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old

@@ -78,9 +78,20 @@ def _gpu_worker(rank, world, port, q):
         ok = True
         for s in range(2):
             _, ind, _ = vq(torch.from_numpy(g[f'r{rank}_x{s}']).cuda())
+            # the statistics all-reduce runs on a side stream and the EMA is deferred until somebody
+            # looks at the codebook (the attribute accesses below)
+            ok &= vq._codebook.__dict__.get('_pending') is not None
             ok &= torch.equal(ind.cpu(), torch.from_numpy(g[f'r{rank}_ind{s}']))
             ok &= torch.allclose(vq._codebook.embed[0].cpu(), torch.from_numpy(g[f'r{rank}_embed{s + 1}']), rtol=1e-4, atol=1e-6)
             ok &= torch.allclose(vq._codebook.cluster_size[0].cpu(), torch.from_numpy(g[f'r{rank}_cluster{s + 1}']), rtol=1e-5, atol=1e-7)
+            ok &= vq._codebook.__dict__.get('_pending') is None
+        # every rank must hold the SAME codebook, bit for bit (the reference's invariant, :419,427)
+        mine = torch.cat([vq._codebook.embed.reshape(-1), vq._codebook.cluster_size.reshape(-1)])
+        lo, hi = mine.clone(), mine.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ok &= torch.equal(lo, hi)
+        sd = vq.state_dict()
+        ok &= torch.equal(sd['_codebook.embed'], vq._codebook.embed)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

@@ -88,3 +88,45 @@ def test_vq_oracle_ddp_fixture(golden_dir):
             torch.testing.assert_close(ne, _t(g[f'r{r}_embed{s + 1}']), rtol=1e-5, atol=1e-6)
             torch.testing.assert_close(nc, _t(g[f'r{r}_cluster{s + 1}']), rtol=1e-6, atol=1e-7)
             embed[r], cluster[r] = ne, nc
+
+
+def big_case_codebook(g):
+    """Regenerate the seeded initial codebook of a vq_big_* fixture (the reference module's own
+    initialisation: kaiming_uniform -> l2norm under torch.manual_seed(seed)) and check it against the
+    recorded digest, so the 16 MB codebook does not have to be stored."""
+    torch.manual_seed(int(g['seed']))
+    e = torch.empty(1, int(g['K']), int(g['D']))
+    torch.nn.init.kaiming_uniform_(e)
+    e = torch.nn.functional.normalize(e, p=2, dim=-1)[0]
+    assert float(e.double().sum()) == pytest.approx(float(g['embed0_sum']), rel=1e-12, abs=1e-9)
+    assert float(e.double().abs().sum()) == pytest.approx(float(g['embed0_abs']), rel=1e-12)
+    assert torch.equal(e[7], _t(g['embed0_row7']))
+    return e
+
+
+@pytest.mark.parametrize('name', ['big_k1024', 'big_k16384', 'big_ortho'])
+def test_vq_oracle_matches_reference_at_production_width(golden_dir, name):
+    """D = 256, K in {1024, 16384}: the shapes the tensor-core search serves, recorded from the
+    reference itself (oracle/make_golden.py: vq_big_case)."""
+    g = _load(golden_dir, name)
+    K = int(g['K'])
+    embed = big_case_codebook(g)
+    x = _t(g['x'])
+    r = vo.vector_quantize_forward(x, embed, torch.zeros(K), training=True, commitment_weight=1.0)
+    assert torch.equal(r['embed_ind'], _t(g['ind']))
+    torch.testing.assert_close(r['quantize'], _t(g['q']), rtol=1e-6, atol=1e-7)
+    rows = _t(g['rows'])
+    torch.testing.assert_close(r['new_embed'][rows], _t(g['embed1_rows']), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(r['new_cluster_size'][rows], _t(g['cluster1_rows']), rtol=1e-6, atol=1e-7)
+    assert float(r['new_embed'].double().sum()) == pytest.approx(float(g['embed1_sum']), rel=1e-6, abs=1e-4)
+    assert float(r['new_cluster_size'].double().sum()) == pytest.approx(float(g['cluster1_sum']), rel=1e-6)
+    loss = r['loss']
+    if float(g['ortho']) > 0:
+        # the reference measures the (1, K, D) codebook along dim 0: the whole updated codebook enters
+        e1 = r['new_embed'].clone().requires_grad_(True)
+        lo = vo.orthogonal_loss(e1) * float(g['ortho'])
+        lo.backward()
+        loss = loss + lo.detach()
+        # the fixture's backward was (q * gq).sum() + 0.7 * loss
+        torch.testing.assert_close(0.7 * e1.grad[rows], _t(g['gembed_rows']), rtol=1e-4, atol=1e-9)
+    torch.testing.assert_close(loss, _t(g['loss']), rtol=1e-5, atol=1e-8)
