@@ -427,6 +427,10 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-kernel-rooflines', action='store_true', help='skip the stand-alone kernel timings')
     ap.add_argument('--microbench', action='store_true', help='BASELINE configs[4]: kernel sweep table')
+    ap.add_argument('--no-graph', dest='graph', action='store_false',
+                    help='time eager steps.  Default: the step (forward, backward, both quantizer calls, the '
+                         'statistics all-reduces when N > 1) is captured in ONE CUDA graph and replays are timed; '
+                         'the per-kernel trace and the launch count are then taken from eager steps')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -467,12 +471,53 @@ def main():
     for _ in range(max(args.warmup, 3)):
         hp.step(inp)
     barrier()
+    graph, graph_note = None, 'eager steps (--no-graph)'
+    if args.graph:
+        # the step has no host synchronisation and no data-dependent host control flow, so
+        # forward + backward + both quantizer calls (and, for N > 1, the two side-stream all-reduces of the
+        # code statistics) replay as one graph launch.  The capture must end with the side stream joined,
+        # so the captured step applies the second EMA update at its end instead of deferring it into the
+        # next step.
+        eager_step = hp.step
+
+        def closed_step(inp_):
+            out = eager_step(inp_)
+            hp.vq._codebook._flush()
+            return out
+        try:
+            side = torch.cuda.Stream(device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    closed_step(inp)
+            torch.cuda.current_stream(device).wait_stream(side)
+            barrier()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                graph_loss = closed_step(inp)
+            hp.step = lambda _inp: (graph.replay(), graph_loss)[1]
+            for _ in range(3):
+                hp.step(inp)
+            graph_note = 'whole step replayed as ONE CUDA graph (roofline_kernels / gpu_launches from eager steps)'
+        except Exception as exc:                          # noqa: BLE001 - fall back to eager, and say so
+            graph = None
+            hp.step = eager_step
+            graph_note = f'eager steps: CUDA graph capture failed ({type(exc).__name__}: {str(exc)[:120]})'
+            torch.cuda.synchronize()
+        ok = torch.tensor([1.0 if graph is not None else 0.0], device=device)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)     # all ranks replay, or none does
+        if float(ok) == 0.0 and graph is not None:
+            graph = None
+            hp.step = eager_step
+            graph_note = 'eager steps: CUDA graph capture failed on another rank'
+        barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     traced = ['favae_ffl_forward', 'favae_blur_diff_forward', 'favae_blur_backward', 'favae_blur_forward',
               'favae_vq_search_tc']
-    if rank == 0:
+    if rank == 0 and graph is None:
         _lib.start_trace(traced)
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -484,8 +529,19 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0
-    trace = _lib.stop_trace() if rank == 0 else {}
+    trace = _lib.stop_trace() if rank == 0 and graph is None else {}
     clocks = sampler.stop() if rank == 0 else None
+    trace_steps = args.steps
+    if graph is not None:
+        launches = (launches if launches else 0)
+        hp.step = eager_step                       # per-kernel timings and the launch count: eager steps
+        l0 = _lib.launch_count()
+        _lib.start_trace(traced)
+        trace_steps = 10
+        for _ in range(trace_steps):
+            hp.step(inp)
+        trace = _lib.stop_trace()
+        launches = (_lib.launch_count() - l0) * args.steps // trace_steps
     t = torch.tensor([ms_total], device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -539,7 +595,7 @@ def main():
 
     if rank == 0:
         line = base_line(args, wl, world, value, ms_step)
-        groups = kernel_groups(trace, wl, args, pk)
+        groups = kernel_groups(trace, wl, args, pk, trace_steps)
         hbm_groups = [g_ for g_ in groups if 'bytes_per_launch' in g_]
         dom = max(hbm_groups, key=lambda g_: g_['ms_per_step']) if hbm_groups else None
         step_bytes = 16.0 * feature_elements(wl) * args.batch
@@ -564,6 +620,7 @@ def main():
                                       'blur fused = 0 extra bytes; whole step incl. quantizer and image FFL'},
             'cpu_baseline': cpu,
         })
+        line['config']['execution'] = graph_note
         if rank_parity is not None:
             line['rank_parity'] = rank_parity
         if not args.no_kernel_rooflines:
@@ -599,10 +656,10 @@ NCU_TRAFFIC = {'blur_backward': (12.0, 'ncu --set full, blur_adjsig_kernel<9,64>
                'ffl2': (15.48, 'ncu --set full, ffl_kernel<256>: 15.48 B/element (profiles/ncu_r1_summary.md)')}
 
 
-def kernel_groups(trace, wl, args, pk):
+def kernel_groups(trace, wl, args, pk, steps):
     """Per kernel family of the level-0 maps: launches, mean device time per launch (CUDA events
     inside the timed steps), algorithmic bytes (SURVEY 8d per-element figures), achieved GB/s."""
-    steps = max(args.steps, 1)
+    steps = max(steps, 1)
     out = []
 
     def add(name, kernel, rows, bytes_per_launch):

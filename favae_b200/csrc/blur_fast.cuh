@@ -192,98 +192,143 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ /*aux*
 // call sites, consumed only by ffl(de, en), losses/vqgan_losses.py:25) written as ONE map.  The spectrum
 // loss sees pred - target only, so the two blurred maps never need to exist: 12 B/element (read enc, read
 // dec, write d) instead of 16 for two blurs, and the loss kernel then reads 4 B/element instead of 8.
-// Same pipeline as blur_fast_kernel<MODE_FWD>, run twice over the strip by the same threads: pass 0 leaves
-// B_enc(enc) in dst, pass 1 computes B_dec(dec) and subtracts what the thread itself stored (each thread
-// re-reads exactly its own 16 bytes per row, so program order makes the store visible; the strip is 32 KB
-// and still sits in L2).  No shared strip buffer (64 KB per CTA would cost two of the five CTAs per SM)
-// and no second register ring.
+//
+// Both maps go through ONE pipeline in lockstep as packed (enc, dec) pairs: every register pair holds
+// the two maps' values of one pixel and every tap is the pair (k_enc[t], k_dec[t]), so one FFMA2 / FADD2
+// filters both maps (same trick as the (value, d/dsigma) pairs of blur_adjsig_kernel, whose structure
+// this kernel shares: cp.async shared-memory rings for the two input streams, KS-row window of pairs in
+// registers, mirrored taps added first, two-plane shared line, KS rows unrolled inside a rolled loop).
+// First version, kept for the record: the forward kernel run twice over the strip by the same threads
+// (pass 0 leaves B_enc(enc) in dst, pass 1 subtracts it): 1.13 ms at 4096 maps of 256^2 with a plain
+// re-load (one exposed L2 round trip per row), 1.00 ms with a cp.async ring, 0.99 ms with evict-first
+// input loads (ncu: 13.5 B/element of DRAM traffic, 166 M warp instructions per 1024 maps, issue active
+// 60 %, `no_instruction` 1.5 cycles per issue: two scalar passes of a fully unrolled 40-row body are
+// instruction bound).
+#ifndef FAVAE_DIFF_MINB
+#define FAVAE_DIFF_MINB 4
+#endif
 template <int KS, int TH>
-__global__ void __launch_bounds__(THREADS, FAVAE_FWD_MINB)
+__global__ void __launch_bounds__(THREADS, KS <= 9 ? FAVAE_DIFF_MINB : KS == 11 ? 3 : 2)   // the window is 8 KS registers
 blur_diff_kernel(const float* __restrict__ enc, const float* __restrict__ dec, int h, int w, long long items,
                  int strips, const float* __restrict__ sigma_enc, const float* __restrict__ sigma_dec,
-                 float* dst) {
+                 float* __restrict__ dst) {
   constexpr int P = KS / 2;
-  extern __shared__ float lines[];               // [2 buffers][groups][w + 2*LPAD]
+  extern __shared__ float lines[];               // as float2: [2 buffers][groups][w + 2*LPAD]
   __shared__ float sk[2][32], sdk[32];
-  float k[KS], dk[KS];
-  load_weights<KS>(sigma_enc, sk[0], sdk, k, dk);
-  load_weights<KS>(sigma_dec, sk[1], sdk, k, dk);
-
-  const int tpi = w >> 2;
+  float2 kk[P + 1];                              // (k_enc[t], k_dec[t]); tap t and tap KS-1-t are equal
+  {
+    float k[KS], dk[KS];
+    load_weights<KS>(sigma_enc, sk[0], sdk, k, dk);
+    load_weights<KS>(sigma_dec, sk[1], sdk, k, dk);
+#pragma unroll
+    for (int t = 0; t <= P; ++t) kk[t] = make_float2(sk[0][t], sk[1][t]);
+  }
+  const int tpi = w >> 2;                        // threads per item
   const int groups = THREADS / tpi;
   const int grp = threadIdx.x / tpi, tx = threadIdx.x % tpi;
   const int x0 = tx * 4;
-  const int ll = w + 2 * LPAD;
+  const int ll = w + 2 * LPAD;                   // float2 per line
+  float2* lines2 = reinterpret_cast<float2*>(lines);
   const long long item = (long long)blockIdx.x * groups + grp;
   const bool live = item < items;
   const long long map = live ? item / strips : 0;
-  const int y0_ = live ? (int)(item % strips) * TH : 0;
+  const int y0 = live ? (int)(item % strips) * TH : 0;
   const long long mapoff = map * (long long)h * w;
-  constexpr int Q = FAVAE_FWD_Q, RS = KS + Q, NR = TH + KS - 1;
-
+  const float* ebase = enc + mapoff;
+  const float* dbase = dec + mapoff;
+  constexpr int GD = 4, RS = KS, NR = TH + KS - 1;
+  __shared__ float4 ering[GD][THREADS], dring[GD][THREADS];
+  auto issue_rows = [&](int r) {
+    if (live && r < NR) {
+      const int slot = r & (GD - 1);
+      const long long off = (long long)reflect_idx(y0 - P + r, h) * w + x0;
+      const unsigned de = (unsigned)__cvta_generic_to_shared(&ering[slot][threadIdx.x]);
+      const unsigned dd = (unsigned)__cvta_generic_to_shared(&dring[slot][threadIdx.x]);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(de), "l"(ebase + off) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dd), "l"(dbase + off) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int q = 0; q < GD - 1; ++q) issue_rows(q);
+  float2 ring[RS][4];
+#pragma unroll
+  for (int q = 0; q < RS; ++q)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ring[q][c] = make_float2(0.f, 0.f);
 #pragma unroll 1
-  for (int which = 0; which < 2; ++which) {
-    const float* base = (which ? dec : enc) + mapoff;
-    float* dbase = dst + mapoff;
-    int y0 = y0_;
-    // opaque per pass: otherwise the row offsets and output addresses of all 40 unrolled rows are
-    // hoisted out of this rolled loop as invariants and spill
-    asm volatile("" : "+l"(dbase), "+r"(y0));
+  for (int r0 = 0; r0 < NR; r0 += RS) {
 #pragma unroll
-    for (int t = 0; t < KS; ++t) k[t] = sk[which][t];
-    auto load_row = [&](int r) -> float4 {
-      const int ry = reflect_idx(y0 - P + r, h);
-      float4 in = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live) in = ld4(base + (long long)ry * w + x0);
-      return in;
-    };
-    float4 ring[RS];
-#pragma unroll
-    for (int q = 0; q < RS; ++q) ring[q] = (q < Q) ? load_row(q) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      const int u = r % RS;
-      if (r + Q < NR) ring[(u + Q) % RS] = load_row(r + Q);
-      if (r < KS - 1) continue;
-      const int yo = y0 + r - (KS - 1);
-      const bool store = live && yo < h;
-      float* out = dbase + (long long)yo * w + x0;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int t = 0; t < KS; ++t) fma4(v, k[t], ring[(u + RS - (KS - 1) + t) % RS]);
-      float* line = lines + (size_t)((r & 1) * groups + grp) * ll;
-      *reinterpret_cast<float4*>(line + LPAD + x0) = v;
+    for (int u = 0; u < RS; ++u) {
+      const int r = r0 + u;
+      if (r >= NR) break;
+      issue_rows(r + GD - 1);
+      asm volatile("cp.async.wait_group %0;" ::"n"(GD - 1) : "memory");
       {
-        const float vv[4] = {v.x, v.y, v.z, v.w};
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f), d = e;
+        if (live) { e = ering[r & (GD - 1)][threadIdx.x]; d = dring[r & (GD - 1)][threadIdx.x]; }
+        ring[u][0] = make_float2(e.x, d.x); ring[u][1] = make_float2(e.y, d.y);
+        ring[u][2] = make_float2(e.z, d.z); ring[u][3] = make_float2(e.w, d.w);
+      }
+      if (r < KS - 1) continue;
+      const int yo = y0 + r - (KS - 1);            // output row of this iteration
+#define FAVAE_WIN(t) ring[(u + 1 + (t)) % RS]
+      // ---- vertical pass over the mirrored window, both maps per instruction
+      float2 acc[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 4; ++c) acc[c] = pk_mul(FAVAE_WIN(P)[c], kk[P]);
+#pragma unroll
+      for (int t = 0; t < P; ++t)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[c] = pk_fma(pk_add(FAVAE_WIN(t)[c], FAVAE_WIN(KS - 1 - t)[c]), kk[t], acc[c]);
+#undef FAVAE_WIN
+      // ---- horizontal pass through a shared line of (enc, dec) pairs: two planes of float4 as in
+      // blur_adjsig_kernel (plane A: columns 4q, 4q+1 of thread q; plane B: columns 4q+2, 4q+3)
+      constexpr int LP = 2, NB = (P + 3) / 4;
+      float4* planeA = reinterpret_cast<float4*>(lines2 + (size_t)((r & 1) * groups + grp) * ll);
+      float4* planeB = planeA + (tpi + 2 * LP);
+      planeA[LP + tx] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+      planeB[LP + tx] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+      if (tx <= P / 4 || tx >= tpi - 1 - P / 4) {   // owners of columns 1..P and w-1-P..w-2
+        auto put = [&](int col, float2 v) {
+          const int q = (col + 4 * LP) / 4 - LP, c = col - 4 * q;
+          float2* pl = reinterpret_cast<float2*>(c < 2 ? planeA : planeB);
+          pl[2 * (LP + q) + (c & 1)] = v;
+        };
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {              // reflect: column -j <- j, column w-1+j <- w-1-j
           const int j = x0 + c;
-          if (j >= 1 && j <= P) line[LPAD - j] = vv[c];
+          if (j >= 1 && j <= P) put(-j, acc[c]);
           const int jr = w - 1 - j;
-          if (jr >= 1 && jr <= P) line[LPAD + w - 1 + jr] = vv[c];
+          if (jr >= 1 && jr <= P) put(w - 1 + jr, acc[c]);
         }
       }
       __syncthreads();
-      // B_enc(enc) of this row, stored by this thread in pass 0.  Requested here, behind the barrier
-      // (an asm volatile load stays put: hoisted to the top of the unrolled strip, 32 of them spill),
-      // and consumed after the horizontal pass.
-      float4 prev = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (which && store)
-        asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(prev.x), "=f"(prev.y), "=f"(prev.z), "=f"(prev.w) : "l"(out) : "memory");
-      float seg[4 + 2 * P];
+      float2 cols[4 * (2 * NB + 1)];               // columns x0 - 4 NB .. x0 + 4 NB + 3; own from registers
 #pragma unroll
-      for (int i = 0; i < 4 + 2 * P; ++i) seg[i] = line[LPAD + x0 - P + i];
-      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int q = -NB; q <= NB; ++q) {
+        float2* dd = cols + 4 * (q + NB);
+        if (q == 0) { dd[0] = acc[0]; dd[1] = acc[1]; dd[2] = acc[2]; dd[3] = acc[3]; }
+        else {
+          const float4 a = planeA[LP + tx + q], b = planeB[LP + tx + q];
+          dd[0] = make_float2(a.x, a.y); dd[1] = make_float2(a.z, a.w);
+          dd[2] = make_float2(b.x, b.y); dd[3] = make_float2(b.z, b.w);
+        }
+      }
+      const float2* seg = cols + (4 * NB - P);     // seg[i] = column x0 - P + i
+      float o[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
+        float2 a2 = pk_mul(seg[c + P], kk[P]);
 #pragma unroll
-        for (int t = 0; t < KS; ++t) o[c] = fmaf(k[t], seg[c + t], o[c]);
+        for (int t = 0; t < P; ++t) a2 = pk_fma(pk_add(seg[c + t], seg[c + KS - 1 - t]), kk[t], a2);
+        o[c] = a2.y - a2.x;                        // B_dec(dec) - B_enc(enc)
       }
-      if (store) *reinterpret_cast<float4*>(out) = make_float4(o[0] - prev.x, o[1] - prev.y, o[2] - prev.z, o[3] - prev.w);
+      if (live && yo < h)
+        __stcs(reinterpret_cast<float4*>(dst + mapoff + (long long)yo * w + x0), make_float4(o[0], o[1], o[2], o[3]));
     }
-    __syncthreads();                              // the line buffers are reused by the second pass
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // MODE_ADJ_SIG rewritten around packed fp32x2 arithmetic (FADD2 / FFMA2 issue two fp32 lanes per
@@ -744,7 +789,7 @@ static int launch_diff_one(const float* enc, const float* dec, long long maps, i
   const int strips = (h + TH - 1) / TH, groups = THREADS / (w / 4);
   const long long items = maps * strips;
   const long long blocks = (items + groups - 1) / groups;
-  const size_t smem = sizeof(float) * 2 * groups * (size_t)(w + 2 * LPAD);
+  const size_t smem = sizeof(float) * 2 * groups * 2 * (size_t)(w + 2 * LPAD);      // lines of (enc, dec) pairs
   blur_diff_kernel<KS, TH><<<(unsigned)blocks, THREADS, smem, s>>>(enc, dec, h, w, items, strips, sigma_enc, sigma_dec, dst);
   return check_launch("blur_diff");
 }
@@ -753,7 +798,8 @@ static int launch_diff(const float* enc, const float* dec, long long maps, int h
 #define FAVAE_BLUR_CASE(KS)                                                                                   \
   case KS:                                                                                                    \
     return h <= 16 ? launch_diff_one<KS, 16>(enc, dec, maps, h, w, sigma_enc, sigma_dec, dst, s)               \
-                   : launch_diff_one<KS, 32>(enc, dec, maps, h, w, sigma_enc, sigma_dec, dst, s);
+         : h >= 128 ? launch_diff_one<KS, 64>(enc, dec, maps, h, w, sigma_enc, sigma_dec, dst, s)              \
+                    : launch_diff_one<KS, 32>(enc, dec, maps, h, w, sigma_enc, sigma_dec, dst, s);
   switch (ks) {
     FAVAE_BLUR_CASE(3)
     FAVAE_BLUR_CASE(5)

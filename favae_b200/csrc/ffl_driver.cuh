@@ -42,7 +42,9 @@ FAVAE_HD void ffl_init_thread(Env& env) {
 
 // Issue the HBM loads of one P1 pass (pred / target rows r', r' + N/2 of every thread group) into
 // ThreadRegs; nothing waits for them here.
-template <class Cfg, class Env>
+// DIFF (compile time): pred already holds the difference map (fused DSL op), there is no target: the
+// ta / tb registers (32 of the 64 that hold a pass in flight at N = 256) and the subtraction vanish.
+template <class Cfg, bool DIFF = false, class Env>
 FAVAE_HD void ffl_issue_loads(Env& env, const FflParams& p, long long batch, int pass) {
   constexpr int N = Cfg::N, TG = Cfg::TG, NG = Cfg::NG, HALF = Cfg::HALF, V4 = Cfg::IO_V4;
   constexpr int GPC = HALF / Cfg::C;
@@ -56,13 +58,15 @@ FAVAE_HD void ffl_issue_loads(Env& env, const FflParams& p, long long batch, int
 #pragma unroll
     for (int j = 0; j < V4; ++j) {
       const int f = t + TG * j;                          // float4 index inside the row
-      r.pa[j] = r.ta[j] = r.pb[j] = r.tb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      r.pa[j] = r.pb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (!DIFF) r.ta[j] = r.tb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (live) {
-        // target == nullptr: pred already holds the difference map (fused DSL op, blur_diff_kernel)
         r.pa[j] = *reinterpret_cast<const float4*>(p.pred + base + 4 * f);
-        if (p.target) r.ta[j] = *reinterpret_cast<const float4*>(p.target + base + 4 * f);
         r.pb[j] = *reinterpret_cast<const float4*>(p.pred + base + HALF * N + 4 * f);
-        if (p.target) r.tb[j] = *reinterpret_cast<const float4*>(p.target + base + HALF * N + 4 * f);
+        if constexpr (!DIFF) {
+          r.ta[j] = *reinterpret_cast<const float4*>(p.target + base + 4 * f);
+          r.tb[j] = *reinterpret_cast<const float4*>(p.target + base + HALF * N + 4 * f);
+        }
       }
     }
   });
@@ -75,8 +79,17 @@ FAVAE_HD void ffl_issue_loads(Env& env, const FflParams& p, long long batch, int
 // m = |D|^2 unnormalised.  The spectrum statistics then run on m (sum m*sqrt(m), max m: the maximum
 // commutes with the monotone f) and are converted once per thread, and the weight is
 // min(sqrt(m) / sqrt(m_max), 1): 5-6 instructions per bin instead of ~12.
-template <class Cfg, bool FAST = false, class Env>
+#ifndef FAVAE_FFL_DIFF_PIPE
+#define FAVAE_FFL_DIFF_PIPE 1
+#endif
+template <class Cfg, bool DIFF> struct FflPipe {
+  // the single-input form has the registers to keep the next map's first pass in flight under the last
+  // gradient stores of the current one (the two-input form spills at 512 threads, see Cfg::PIPELINE_LOADS)
+  static constexpr bool value = Cfg::PIPELINE_LOADS || (DIFF && Cfg::C == 2 && FAVAE_FFL_DIFF_PIPE);
+};
+template <class Cfg, bool FAST = false, bool DIFF = false, class Env>
 FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long long next_batch = -1) {
+  constexpr bool PIPE = FflPipe<Cfg, DIFF>::value;
   constexpr int N = Cfg::N, R1 = Cfg::R1, TG = Cfg::TG, NG = Cfg::NG, HALF = Cfg::HALF;
   constexpr int C = Cfg::C, MPC = Cfg::MPC, T = Cfg::THREADS, PASSES = Cfg::PASSES;
   constexpr int GPC = HALF / C;                 // row pairs / column groups per CTA and map
@@ -100,7 +113,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
   constexpr int V4 = Cfg::IO_V4;
   constexpr int IOB4 = Cfg::IO_B2 / 2;          // float4 index of the second half of the I/O staging
   for (int pass = 0; pass < PASSES; ++pass) {
-    if (pass > 0 || !Cfg::PIPELINE_LOADS) ffl_issue_loads<Cfg>(env, p, batch, pass);
+    if (pass > 0 || !PIPE) ffl_issue_loads<Cfg, DIFF>(env, p, batch, pass);
     env.for_threads([&](int cta, int tid) {
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
       const int g = tid / TG, t = tid % TG;
@@ -109,8 +122,11 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
 #pragma unroll
       for (int j = 0; j < V4; ++j) {
         const int f = t + TG * j;
-        const float4 a = make_float4(pa[j].x - ta[j].x, pa[j].y - ta[j].y, pa[j].z - ta[j].z, pa[j].w - ta[j].w);
-        const float4 b = make_float4(pb[j].x - tb[j].x, pb[j].y - tb[j].y, pb[j].z - tb[j].z, pb[j].w - tb[j].w);
+        float4 a = pa[j], b = pb[j];
+        if constexpr (!DIFF) {
+          a = make_float4(pa[j].x - ta[j].x, pa[j].y - ta[j].y, pa[j].z - ta[j].z, pa[j].w - ta[j].w);
+          b = make_float4(pb[j].x - tb[j].x, pb[j].y - tb[j].y, pb[j].z - tb[j].z, pb[j].w - tb[j].w);
+        }
         if constexpr (Cfg::R2 > 1) {                     // interleave (row r', row r'+N/2) pairs
           stg4[f] = make_float4(a.x, b.x, a.y, b.y);          // elements 4f, 4f+1
           stg4[IOB4 + f] = make_float4(a.z, b.z, a.w, b.w);   // elements 4f+2, 4f+3 (bank-shifted half)
@@ -166,12 +182,12 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
         const long long nmaps = (p.maps - next_batch * MPC < MPC) ? p.maps - next_batch * MPC : MPC;
         if constexpr (C == 1) {
           env.prefetch_l2(p.pred + next_batch * MPC * (long long)(N * N), nmaps * N * N * sizeof(float));
-          if (p.target) env.prefetch_l2(p.target + next_batch * MPC * (long long)(N * N), nmaps * N * N * sizeof(float));
+          if (!DIFF) env.prefetch_l2(p.target + next_batch * MPC * (long long)(N * N), nmaps * N * N * sizeof(float));
         } else {
           const long long base = next_batch * (long long)(N * N) + (long long)cta * GPC * N;
           env.prefetch_l2(p.pred + base, GPC * N * sizeof(float));
           env.prefetch_l2(p.pred + base + HALF * N, GPC * N * sizeof(float));
-          if (p.target) {
+          if (!DIFF) {
             env.prefetch_l2(p.target + base, GPC * N * sizeof(float));
             env.prefetch_l2(p.target + base + HALF * N, GPC * N * sizeof(float));
           }
@@ -357,7 +373,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
   });
   if (p.grad_pred == nullptr && p.grad_target == nullptr) {
     env.for_threads([&](int, int) { env.cluster_arrive_relaxed(); });     // S is not read again
-    if (Cfg::PIPELINE_LOADS && next_batch >= 0) ffl_issue_loads<Cfg>(env, p, next_batch, 0);
+    if (PIPE && next_batch >= 0) ffl_issue_loads<Cfg, DIFF>(env, p, next_batch, 0);
     return;
   }
 
@@ -504,7 +520,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
     env.mark(9);
     if (pass + 1 < PASSES) gather(pass + 1);
     // the next batch's first rows start their trip from HBM / L2 under this pass's gradient stores
-    if (Cfg::PIPELINE_LOADS && pass == PASSES - 1 && next_batch >= 0) ffl_issue_loads<Cfg>(env, p, next_batch, 0);
+    if (PIPE && pass == PASSES - 1 && next_batch >= 0) ffl_issue_loads<Cfg, DIFF>(env, p, next_batch, 0);
     env.for_threads([&](int cta, int tid) {
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
       const int g = tid / TG, t = tid % TG, item = pass * NG + g;

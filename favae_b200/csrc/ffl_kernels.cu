@@ -111,7 +111,7 @@ template <class Cfg> struct DevEnv {
 __device__ long long favae_ffl_phase_cycles[16 * 1024];
 #endif
 
-template <class Cfg, bool FAST>
+template <class Cfg, bool FAST, bool DIFF = false>
 __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 256 && Cfg::SMEM_BYTES < 110 * 1024) ? 2 : 1)
 ffl_kernel(const FflParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -133,9 +133,9 @@ ffl_kernel(const FflParams p) {
   const long long batches = (p.maps + Cfg::MPC - 1) / Cfg::MPC;
   const long long stride = gridDim.x / Cfg::C;
   const long long first = blockIdx.x / Cfg::C;
-  if (Cfg::PIPELINE_LOADS && first < batches) ffl_issue_loads<Cfg>(env, p, first, 0);
+  if (FflPipe<Cfg, DIFF>::value && first < batches) ffl_issue_loads<Cfg, DIFF>(env, p, first, 0);
   for (long long b = first; b < batches; b += stride)
-    ffl_map_batch<Cfg, FAST>(env, p, b, b + stride < batches ? b + stride : -1);
+    ffl_map_batch<Cfg, FAST, DIFF>(env, p, b, b + stride < batches ? b + stride : -1);
   env.cluster_wait();                            // nobody leaves while a peer may still read its S
 #ifdef FAVAE_FFL_TIMING
   __syncthreads();
@@ -143,10 +143,10 @@ ffl_kernel(const FflParams p) {
 #endif
 }
 
-template <class Cfg, bool FAST> static int launch_ffl_impl(const FflParams& p, cudaStream_t stream) {
+template <class Cfg, bool FAST, bool DIFF> static int launch_ffl_impl(const FflParams& p, cudaStream_t stream) {
   static PerDevice<bool> configured_dev;
   bool& configured = configured_dev.here();
-  auto kern = ffl_kernel<Cfg, FAST>;
+  auto kern = ffl_kernel<Cfg, FAST, DIFF>;
   if (!configured) {
     FAVAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Cfg::SMEM_BYTES));
@@ -189,8 +189,10 @@ template <class Cfg, bool FAST> static int launch_ffl_impl(const FflParams& p, c
 
 // alpha == 1 without log weighting (every call site of the reference) takes the lean statistics path
 template <class Cfg> static int launch_ffl(const FflParams& p, cudaStream_t stream) {
-  return (p.alpha == 1.0f && !p.log_matrix && p.grad_scale >= 0.0f) ? launch_ffl_impl<Cfg, true>(p, stream)
-                                                                    : launch_ffl_impl<Cfg, false>(p, stream);
+  const bool fast = p.alpha == 1.0f && !p.log_matrix && p.grad_scale >= 0.0f;
+  if (p.target == nullptr)       // pred holds the difference map (fused DSL level)
+    return fast ? launch_ffl_impl<Cfg, true, true>(p, stream) : launch_ffl_impl<Cfg, false, true>(p, stream);
+  return fast ? launch_ffl_impl<Cfg, true, false>(p, stream) : launch_ffl_impl<Cfg, false, false>(p, stream);
 }
 
 }  // namespace favae

@@ -25,8 +25,10 @@ def recon_ffl_features_loss(ffl, en_feat, de_feat, device):            # :18-30
     de_feat.reverse()
     loss = torch.zeros(1, device=device)
     losses = []
-    inv = torch.tensor(1.0) / len(en_feat)          # the float32 factor `loss / len` applies
-    with expected_upstream_scale(float(inv)):
+    n = len(en_feat)
+    # `loss / len` (:28): the float32 factor autograd will hand back, announced to the loss so that its
+    # forward kernel writes final gradients (no host-device traffic here: the step stays graph-capturable)
+    with expected_upstream_scale(float(torch.tensor(1.0) / n)):
         for i in range(len(en_feat)):
             if fusable(ffl, de_feat[i], en_feat[i]):
                 level = dsl_level_loss(ffl, de_feat[i], en_feat[i])
@@ -34,7 +36,7 @@ def recon_ffl_features_loss(ffl, en_feat, de_feat, device):            # :18-30
                 level = ffl(de_feat[i], en_feat[i])
             loss = loss + level
             losses.append(level)
-    loss = loss * inv.to(loss.device)
+    loss = loss / n
     return loss, losses
 
 
@@ -42,13 +44,13 @@ def recon_sl_gaussian_features_loss(ffl, gaussian_kernel, gaussian_sigma, en_fea
     de_feat.reverse()
     loss = torch.zeros(1, device=device)
     losses = []
-    inv = torch.tensor(1.0) / len(en_feat)
-    with expected_upstream_scale(float(inv)):
+    n = len(en_feat)
+    with expected_upstream_scale(float(torch.tensor(1.0) / n)):
         for i in range(len(en_feat)):
             e = gaussian_blur_reflect(en_feat[i], float(gaussian_sigma), gaussian_kernel)
             d = gaussian_blur_reflect(de_feat[i], float(gaussian_sigma), gaussian_kernel)
             level = ffl(d, e)
             loss = loss + level
             losses.append(level)
-    loss = loss * inv.to(loss.device)
+    loss = loss / n
     return loss, losses

@@ -43,7 +43,7 @@ def main():
 
     shape = (B, 128, 256, 256)
     E = B * 128 * 256 * 256
-    if want('ffl') or want('blur_fwd') or want('blur_bwd'):
+    if want('ffl') or want('blur_fwd') or want('blur_bwd') or want('blur_diff'):
         p = torch.randn(shape, device=dev); t = torch.randn(shape, device=dev)
         gp = torch.empty_like(p); gt = torch.empty_like(p)
         sig = torch.tensor(3.0, device=dev)
@@ -55,6 +55,15 @@ def main():
         ms = timed(lambda: _lib.call('favae_ffl_forward', p.data_ptr(), t.data_ptr(), B * 128, 256, 256, 1.0, 0,
                                      1e-3, ml.data_ptr(), None, None, None, None, st()), it)
         print(f'ffl_256 loss only  {ms:8.3f} ms  {8 * E / ms / 1e6:8.1f} GB/s algorithmic (8 B/elem)')
+        # fused DSL level: single-input form (pred holds the difference map), gradient written in place
+        d = p.clone()
+        ms = timed(lambda: _lib.call('favae_ffl_forward', d.data_ptr(), None, B * 128, 256, 256, 1.0, 0,
+                                     1e-3, ml.data_ptr(), d.data_ptr(), None, None, None, st()), it)
+        print(f'ffl_256 d -> G in place {ms:8.3f} ms  {8 * E / ms / 1e6:8.1f} GB/s algorithmic (8 B/elem)')
+        ms = timed(lambda: _lib.call('favae_ffl_forward', p.data_ptr(), None, B * 128, 256, 256, 1.0, 0,
+                                     1e-3, ml.data_ptr(), gp.data_ptr(), None, None, None, st()), it)
+        print(f'ffl_256 d -> G          {ms:8.3f} ms  {8 * E / ms / 1e6:8.1f} GB/s algorithmic (8 B/elem)')
+        del d
         p16 = torch.randn(B * 512, 1, 16, 16, device=dev); t16 = torch.randn_like(p16)
         g16 = torch.empty_like(p16); h16 = torch.empty_like(p16); ml16 = torch.empty(B * 512, device=dev)
         ms = timed(lambda: _lib.call('favae_ffl_forward', p16.data_ptr(), t16.data_ptr(), B * 512, 16, 16, 1.0, 0,
@@ -64,14 +73,19 @@ def main():
         ms = timed(lambda: _lib.call('favae_blur_forward', p.data_ptr(), B * 128, 256, 256, 9, sig.data_ptr(),
                                      gp.data_ptr(), st()), it)
         print(f'blur fwd k9        {ms:8.3f} ms  {8 * E / ms / 1e6:8.1f} GB/s (8 B/elem)')
+    if want('blur_diff'):
+        sig2 = torch.tensor(2.5, device=dev)
+        ms = timed(lambda: _lib.call('favae_blur_diff_forward', p.data_ptr(), t.data_ptr(), B * 128, 256, 256, 9,
+                                     sig.data_ptr(), sig2.data_ptr(), gp.data_ptr(), st()), it)
+        print(f'blur diff k9       {ms:8.3f} ms  {12 * E / ms / 1e6:8.1f} GB/s (12 B/elem)')
     if want('blur_bwd'):
         gs = torch.empty(1, device=dev)
         parts = torch.empty(int(_lib.load().favae_blur_partials(B * 128, 256, 256)), device=dev)
         ms = timed(lambda: _lib.call('favae_blur_backward', t.data_ptr(), p.data_ptr(), B * 128, 256, 256, 9,
-                                     sig.data_ptr(), gp.data_ptr(), gs.data_ptr(), parts.data_ptr(), st()), it)
+                                     sig.data_ptr(), 1.0, gp.data_ptr(), gs.data_ptr(), parts.data_ptr(), st()), it)
         print(f'blur bwd+sigma k9  {ms:8.3f} ms  {12 * E / ms / 1e6:8.1f} GB/s (12 B/elem)')
         ms = timed(lambda: _lib.call('favae_blur_backward', t.data_ptr(), p.data_ptr(), B * 128, 256, 256, 9,
-                                     sig.data_ptr(), gp.data_ptr(), None, None, st()), it)
+                                     sig.data_ptr(), 1.0, gp.data_ptr(), None, None, st()), it)
         print(f'blur bwd k9        {ms:8.3f} ms  {8 * E / ms / 1e6:8.1f} GB/s (8 B/elem)')
     if want('small'):
         # the three 16 x 16 feature levels of the f=16 model: B*512, B*512, B*256 maps
@@ -85,7 +99,7 @@ def main():
                                          ys.data_ptr(), st()), it)
             print(f'blur16 fwd  maps={maps:6d} {ms * 1e3:8.1f} us')
             ms = timed(lambda: _lib.call('favae_blur_backward', gs_.data_ptr(), xs.data_ptr(), maps, 16, 16, 9,
-                                         sg.data_ptr(), ys.data_ptr(), g1.data_ptr(), parts.data_ptr(), st()), it)
+                                         sg.data_ptr(), 1.0, ys.data_ptr(), g1.data_ptr(), parts.data_ptr(), st()), it)
             print(f'blur16 bwd+sigma maps={maps:6d} {ms * 1e3:8.1f} us')
             ms = timed(lambda: _lib.call('favae_ffl_forward', xs.data_ptr(), gs_.data_ptr(), maps, 16, 16, 1.0, 0,
                                          1e-3, ml.data_ptr(), gp2.data_ptr(), gt2.data_ptr(), None, None, st()), it)
@@ -104,7 +118,7 @@ def main():
                                          ys.data_ptr(), st()), it)
             print(f'blur64 fwd k{ks}        {ms:8.3f} ms  {8 * E4 / ms / 1e6:8.1f} GB/s (8 B/elem)')
             ms = timed(lambda: _lib.call('favae_blur_backward', gs_.data_ptr(), xs.data_ptr(), maps, 64, 64, ks,
-                                         sg.data_ptr(), ys.data_ptr(), g1.data_ptr(), parts.data_ptr(), st()), it)
+                                         sg.data_ptr(), 1.0, ys.data_ptr(), g1.data_ptr(), parts.data_ptr(), st()), it)
             print(f'blur64 bwd+sigma k{ks}  {ms:8.3f} ms  {12 * E4 / ms / 1e6:8.1f} GB/s (12 B/elem)')
         ms = timed(lambda: _lib.call('favae_ffl_forward', xs.data_ptr(), gs_.data_ptr(), maps, 64, 64, 1.0, 0,
                                      1e-3, ml.data_ptr(), gp2.data_ptr(), gt2.data_ptr(), None, None, st()), it)

@@ -50,17 +50,22 @@ template <class Cfg> struct HostEnv {
   }
 };
 
-template <class Cfg> static void run(const FflParams& p) {
+template <class Cfg, bool DIFF> static void run_form(const FflParams& p) {
   HostEnv<Cfg> env;
   ffl_init_thread<Cfg>(env);
   const long long batches = (p.maps + Cfg::MPC - 1) / Cfg::MPC;
   const bool fast = p.alpha == 1.0f && !p.log_matrix && p.grad_scale >= 0.0f;     // same dispatch as ffl_kernels.cu
-  if (Cfg::PIPELINE_LOADS && batches > 0) ffl_issue_loads<Cfg>(env, p, 0, 0);
+  if (FflPipe<Cfg, DIFF>::value && batches > 0) ffl_issue_loads<Cfg, DIFF>(env, p, 0, 0);
   for (long long b = 0; b < batches; ++b) {
     const long long nb = b + 1 < batches ? b + 1 : -1;
-    if (fast) ffl_map_batch<Cfg, true>(env, p, b, nb);
-    else ffl_map_batch<Cfg, false>(env, p, b, nb);
+    if (fast) ffl_map_batch<Cfg, true, DIFF>(env, p, b, nb);
+    else ffl_map_batch<Cfg, false, DIFF>(env, p, b, nb);
   }
+}
+// target == nullptr: the single-input form (pred is the difference map), as in ffl_kernels.cu
+template <class Cfg> static void run(const FflParams& p) {
+  if (p.target == nullptr) run_form<Cfg, true>(p);
+  else run_form<Cfg, false>(p);
 }
 
 extern "C" int ffl_emul(int n, const float* pred, const float* target, long long maps, float alpha,

@@ -53,6 +53,25 @@ def test_emulated_kernel_matches_oracle(emul, n, maps, alpha, logm):
     assert (gt.double() - td.grad).abs().max() <= 1e-5 * scale
 
 
+@pytest.mark.parametrize('n,maps', [(16, 33), (64, 3), (256, 3), (512, 1)])
+def test_emulated_single_input_form_in_place(emul, n, maps):
+    """target == NULL: pred holds the difference map and the gradient G = dL/d(difference) overwrites it
+    in place (the fused DSL level); N = 256 also runs the pipelined loads of the next map."""
+    g = torch.Generator().manual_seed(n)
+    p = torch.randn(maps, 1, n, n, generator=g)
+    t = torch.randn(maps, 1, n, n, generator=g)
+    d = (p - t).contiguous()
+    ml = torch.full((maps,), float('nan'))
+    lw = 0.5
+    gs = 2 * lw / p.numel() / (n * n)
+    assert emul.ffl_emul(n, d.data_ptr(), None, maps, 1.0, 0, gs, d.data_ptr(), None, ml.data_ptr(), None, None) == 0
+    pd = p.double().requires_grad_(True)
+    ref = fo.focal_frequency_loss(pd, t.double(), loss_weight=lw)
+    ref.backward()
+    assert abs((ml.double().sum() * lw / p.numel()).item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert (d.double() - pd.grad).abs().max() <= 1e-5 * pd.grad.abs().max()
+
+
 def test_emulated_identical_inputs(emul):
     p = torch.randn(3, 1, 16, 16)
     gp = torch.full_like(p, float('nan')); ml = torch.full((3,), float('nan'))

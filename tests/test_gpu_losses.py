@@ -16,21 +16,31 @@ EPS32 = 2.0 ** -24
 
 
 def sigma_grad_reference(x, go, sigma, k):
-    """fp64 value of d<go, blur(x; sigma)>/dsigma = sum_i go_i u_i (u = d blur / d sigma, forward-mode
-    through the oracle) and sum_i |go_i u_i|.  The second number is the conditioning of the sum: an fp32
-    evaluation of it (4-9 roundings per product, tree summation) cannot be closer than a few eps32 of
-    it, whatever the algorithm -- with zero-mean random go the sum cancels to ~1/sqrt(N) of it."""
+    """fp64 value of d<go, blur(x; sigma)>/dsigma = sum_j go_j u_j with u = (V'H + VH') x (forward-mode
+    through the oracle), and the running-error scale of that sum,
+        A = sum_j |go_j| * ((|V'| H + V |H'|) |x|)_j,
+    i.e. the same double sum with every term replaced by its magnitude.  The taps k' = dk/dsigma sum to
+    zero (the taps k sum to one for every sigma), so u_j itself is a cancelling sum, and so is the
+    outer one for zero-mean go: an fp32 evaluation in ANY order carries an error of a few eps32 * A
+    (standard dot-product bound), however small the result gets."""
+    import torch.nn.functional as F
     xd, god = x.double(), go.double()
     sd = torch.as_tensor(sigma, dtype=torch.float64, device=xd.device)
     _, u = torch.func.jvp(lambda s: bo.gaussian_blur_reflect(xd, s, k), (sd,), (torch.ones_like(sd),))
-    t = god * u
-    return float(t.sum()), float(t.abs().sum())
+    k1, dk1 = torch.func.jvp(lambda s: bo.gaussian_kernel1d(k, s, torch.float64), (sd,), (torch.ones_like(sd),))
+    k2 = (dk1.abs()[:, None] @ k1[None, :] + k1[:, None] @ dk1.abs()[None, :]).to(xd.device)
+    c = xd.shape[-3]
+    xa = F.pad(xd.abs().reshape(-1, c, *xd.shape[-2:]), [k // 2] * 4, mode='reflect')
+    a = F.conv2d(xa, k2.repeat(c, 1, 1, 1), groups=c).reshape(xd.shape)
+    return float((god * u).sum()), float((god.abs() * a).sum())
 
 
-def assert_sigma_grad(got, ref, sum_abs):
-    """north_star tolerance (1e-4 relative) plus the fp32 floor of the sum: 8 eps32 * sum |terms|
-    (measured: profiles/sigma_grad_error_r2.txt, worst observed 1.4 eps32 * sum |terms|)."""
-    assert abs(float(got) - ref) <= RTOL * abs(ref) + 8 * EPS32 * sum_abs, (float(got), ref, sum_abs)
+def assert_sigma_grad(got, ref, scale):
+    """north_star tolerance (1e-4 relative) plus the fp32 running-error floor 8 eps32 * A (see
+    sigma_grad_reference; measured worst case 3.3 eps32 * A -- generic kernel, k = 15 -- and 0.7 for the
+    streaming kernels over the shapes of profiles/sigma_grad_error_r2.txt, random and all-positive
+    inputs; with random inputs the measured relative error is 1e-9 .. 3e-6)."""
+    assert abs(float(got) - ref) <= RTOL * abs(ref) + 8 * EPS32 * scale, (float(got), ref, scale)
 
 
 def _run(shape, seed=0, **kw):
@@ -144,7 +154,7 @@ def test_blur_matches_reference_fixture(golden_dir):
         ref, sum_abs = sigma_grad_reference(torch.from_numpy(g[f'x{i}']), torch.from_numpy(g[f'go{i}']),
                                             float(g[f'sigma{i}']), int(g[f'k{i}']))
         assert_sigma_grad(sig.grad[1], ref, sum_abs)
-        assert abs(float(g[f'gsig{i}']) - ref) <= 10 * RTOL * abs(ref) + 64 * EPS32 * sum_abs
+        assert abs(float(g[f'gsig{i}']) - ref) <= 10 * RTOL * abs(ref) + 32 * EPS32 * sum_abs
         assert float(sig.grad[0]) == 0.0
 
 
@@ -167,14 +177,18 @@ def test_blur_vs_oracle(shape, k):
     assert (y.cpu().double() - yd).abs().max() <= RTOL * yd.abs().max()
     assert (xg.grad.cpu().double() - xd.grad).abs().max() <= RTOL * xd.grad.abs().max()
     ref, sum_abs = sigma_grad_reference(x, go, 3.0, k)
-    assert float(sd.grad) == pytest.approx(ref, rel=1e-9, abs=1e-12 * sum_abs)     # reverse == forward mode
+    assert float(sd.grad) == pytest.approx(ref, rel=1e-9, abs=1e-13 * sum_abs)     # reverse == forward mode
     assert_sigma_grad(sg.grad, ref, sum_abs)
-    # a well-conditioned sum (all terms of one sign) must meet the plain 1e-4
-    xp, gp = x.abs() + 1.0, go.abs() + 0.5
-    refp, sum_absp = sigma_grad_reference(xp, gp, 3.0, k)
-    xg2 = xp.cuda().requires_grad_(True); sg2 = torch.tensor(3.0, device='cuda', requires_grad=True)
-    (gaussian_blur_reflect(xg2, sg2, k) * gp.cuda()).sum().backward()
-    assert_sigma_grad(sg2.grad, refp, sum_absp)
+    # a well-conditioned sum -- upstream gradient aligned with d blur / d sigma, so that every term of
+    # the outer sum is positive -- meets the plain 1e-4 (the floor is then ~1e-6 of the result)
+    _, u = torch.func.jvp(lambda s: bo.gaussian_blur_reflect(x.double(), s, k),
+                          (torch.tensor(3.0, dtype=torch.float64),), (torch.tensor(1.0, dtype=torch.float64),))
+    gu = u.float()
+    refp, scalep = sigma_grad_reference(x, gu, 3.0, k)
+    assert 8 * EPS32 * scalep < 0.5 * RTOL * abs(refp)
+    xg2 = x.cuda().requires_grad_(True); sg2 = torch.tensor(3.0, device='cuda', requires_grad=True)
+    (gaussian_blur_reflect(xg2, sg2, k) * gu.cuda()).sum().backward()
+    assert abs(float(sg2.grad) - refp) <= RTOL * abs(refp)
 
 
 def test_wrappers_match_reference_fixture(golden_dir):

@@ -376,10 +376,11 @@ def test_deterministic_statistics_mode(monkeypatch):
     torch.testing.assert_close(ca, cc, rtol=0, atol=0)      # counts are exact either way
 
 
-def test_cached_codebook_rows_are_bit_identical_and_invalidate():
+def test_cached_codebook_rows_are_bit_identical_and_invalidate(monkeypatch):
     """The EMA kernel emits l2norm(updated codebook) for the next search; those rows must equal a fresh
     preparation bit for bit, and any torch-side write to ``embed`` must invalidate them."""
     from favae_b200 import VectorQuantize
+    monkeypatch.setenv('FAVAE_VQ_DETERMINISTIC', '1')     # bitwise comparison of two runs below
     torch.manual_seed(1)
     vq = VectorQuantize(dim=256, codebook_size=1024, accept_image_fmap=True, use_cosine_sim=True).cuda().train()
     cb = vq._codebook
