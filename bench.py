@@ -449,7 +449,8 @@ def main():
     import torch.distributed as dist
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=device)
+        import datetime
+        dist.init_process_group('nccl', device_id=device, timeout=datetime.timedelta(seconds=240))
     from favae_b200 import _lib
     pk = peaks()
 
@@ -644,10 +645,21 @@ def main():
                 'workload': w_, 'microbench_large_n': vq_line(262144, big_ms)}
         print(json.dumps(line), flush=True)
     if world > 1:
-        if rank_parity is not None and not rank_parity.startswith('ok'):
-            dist.destroy_process_group()
-            raise SystemExit(f'rank parity check failed: {rank_parity}')
-        dist.destroy_process_group()
+        # Tear-down: the CUDA graph holds captured NCCL kernels; destroying the process group with the
+        # graph still alive left the NCCL watchdog of one rank stuck (observed at N = 2).  Drop the graph
+        # first, agree that everybody is done, and leave without running destructors.
+        failed = rank_parity is not None and not rank_parity.startswith('ok')
+        hp.step = None
+        if graph is not None:
+            graph.reset()
+        graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if failed and rank == 0:
+            print(f'rank parity check failed: {rank_parity}', file=sys.stderr, flush=True)
+        os._exit(1 if failed else 0)
 
 
 # ncu --set full captures of this round (profiles/ncu_r2_summary.md): dram__bytes_read+write per element

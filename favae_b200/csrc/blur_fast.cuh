@@ -188,6 +188,45 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ /*aux*
   }
 }
 
+// Reflect halo of a two-plane shared line of float2 pairs (plane A: columns 4q, 4q+1 of thread q; plane
+// B: columns 4q+2, 4q+3): column -j <- j and column w-1+j <- w-1-j for j = 1..P.  Only the two threads at
+// either end of a row own such columns, and relative to the writer's own slot every destination is a
+// compile-time constant, so the halo costs four thread-role tests per row plus a few stores with
+// immediate offsets on the border threads (the generic per-column test / index arithmetic was ~40 of
+// the ~210 instructions of a row iteration in every warp, since each 32-thread half row owns a border).
+// pa / pb: the writer's own float4 slots in the two planes.
+template <int REL> __device__ __forceinline__ void halo_put_rel(float4* pa, float4* pb, float2 v) {
+  constexpr int Q = REL >= 0 ? REL / 4 : -((-REL + 3) / 4);   // float4 slot relative to the writer's
+  constexpr int C = REL - 4 * Q;                               // column inside that slot
+  reinterpret_cast<float2*>((C < 2 ? pa : pb) + Q)[C & 1] = v;
+}
+template <int P> __device__ __forceinline__ void halo_puts(float4* pa, float4* pb, int tx, int tpi,
+                                                           const float2 (&acc)[4]) {
+  static_assert(P <= 7, "two border threads per side cover at most 7 halo columns");
+  if (tx == 0) {                                   // columns 1..3 -> -1..-3
+    if constexpr (P >= 1) halo_put_rel<-1>(pa, pb, acc[1]);
+    if constexpr (P >= 2) halo_put_rel<-2>(pa, pb, acc[2]);
+    if constexpr (P >= 3) halo_put_rel<-3>(pa, pb, acc[3]);
+  }
+  if (tx == 1) {                                   // columns 4..7 -> -4..-7 (own x0 = 4)
+    if constexpr (P >= 4) halo_put_rel<-8>(pa, pb, acc[0]);
+    if constexpr (P >= 5) halo_put_rel<-9>(pa, pb, acc[1]);
+    if constexpr (P >= 6) halo_put_rel<-10>(pa, pb, acc[2]);
+    if constexpr (P >= 7) halo_put_rel<-11>(pa, pb, acc[3]);
+  }
+  if (tx == tpi - 1) {                             // columns w-2..w-4 -> w..w+2 (own x0 = w - 4)
+    if constexpr (P >= 1) halo_put_rel<4>(pa, pb, acc[2]);
+    if constexpr (P >= 2) halo_put_rel<5>(pa, pb, acc[1]);
+    if constexpr (P >= 3) halo_put_rel<6>(pa, pb, acc[0]);
+  }
+  if (tx == tpi - 2) {                             // columns w-5..w-8 -> w+3..w+6 (own x0 = w - 8)
+    if constexpr (P >= 4) halo_put_rel<11>(pa, pb, acc[3]);
+    if constexpr (P >= 5) halo_put_rel<12>(pa, pb, acc[2]);
+    if constexpr (P >= 6) halo_put_rel<13>(pa, pb, acc[1]);
+    if constexpr (P >= 7) halo_put_rel<14>(pa, pb, acc[0]);
+  }
+}
+
 // d = B_dec(dec) - B_enc(enc): the blurred pair of the DSL (models/vqgan_fcm.py:131-134 and the codec
 // call sites, consumed only by ffl(de, en), losses/vqgan_losses.py:25) written as ONE map.  The spectrum
 // loss sees pred - target only, so the two blurred maps never need to exist: 12 B/element (read enc, read
@@ -289,20 +328,7 @@ blur_diff_kernel(const float* __restrict__ enc, const float* __restrict__ dec, i
       float4* planeB = planeA + (tpi + 2 * LP);
       planeA[LP + tx] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
       planeB[LP + tx] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
-      if (tx <= P / 4 || tx >= tpi - 1 - P / 4) {   // owners of columns 1..P and w-1-P..w-2
-        auto put = [&](int col, float2 v) {
-          const int q = (col + 4 * LP) / 4 - LP, c = col - 4 * q;
-          float2* pl = reinterpret_cast<float2*>(c < 2 ? planeA : planeB);
-          pl[2 * (LP + q) + (c & 1)] = v;
-        };
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {              // reflect: column -j <- j, column w-1+j <- w-1-j
-          const int j = x0 + c;
-          if (j >= 1 && j <= P) put(-j, acc[c]);
-          const int jr = w - 1 - j;
-          if (jr >= 1 && jr <= P) put(w - 1 + jr, acc[c]);
-        }
-      }
+      halo_puts<P>(planeA + LP + tx, planeB + LP + tx, tx, tpi, acc);
       __syncthreads();
       float2 cols[4 * (2 * NB + 1)];               // columns x0 - 4 NB .. x0 + 4 NB + 3; own from registers
 #pragma unroll
@@ -523,20 +549,7 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
       float4* planeB = planeA + (tpi + 2 * LP);
       planeA[LP + tx] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
       planeB[LP + tx] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
-      if (tx <= P / 4 || tx >= tpi - 1 - P / 4) {   // owners of columns 1..P and w-1-P..w-2
-        auto put = [&](int col, float2 v) {        // pair of map column col (halo columns included)
-          const int q = (col + 4 * LP) / 4 - LP, c = col - 4 * q;
-          float2* pl = reinterpret_cast<float2*>(c < 2 ? planeA : planeB);
-          pl[2 * (LP + q) + (c & 1)] = v;
-        };
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {              // reflect: column -j <- j, column w-1+j <- w-1-j
-          const int j = x0 + c;
-          if (j >= 1 && j <= P) put(-j, acc[c]);
-          const int jr = w - 1 - j;
-          if (jr >= 1 && jr <= P) put(w - 1 + jr, acc[c]);
-        }
-      }
+      halo_puts<P>(planeA + LP + tx, planeB + LP + tx, tx, tpi, acc);
       __syncthreads();
       float2 cols[4 * (2 * NB + 1)];               // columns x0 - 4 NB .. x0 + 4 NB + 3; own from registers
 #pragma unroll
@@ -690,20 +703,7 @@ blur_sigma_kernel(const float* __restrict__ src, const float* __restrict__ aux, 
       float4* planeB = planeA + (tpi + 2 * LP);
       planeA[LP + tx] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
       planeB[LP + tx] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
-      if (tx <= P / 4 || tx >= tpi - 1 - P / 4) {   // owners of columns 1..P and w-1-P..w-2
-        auto put = [&](int col, float2 v) {        // pair of map column col (halo columns included)
-          const int q = (col + 4 * LP) / 4 - LP, c = col - 4 * q;
-          float2* pl = reinterpret_cast<float2*>(c < 2 ? planeA : planeB);
-          pl[2 * (LP + q) + (c & 1)] = v;
-        };
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {              // reflect: column -j <- j, column w-1+j <- w-1-j
-          const int j = x0 + c;
-          if (j >= 1 && j <= P) put(-j, acc[c]);
-          const int jr = w - 1 - j;
-          if (jr >= 1 && jr <= P) put(w - 1 + jr, acc[c]);
-        }
-      }
+      halo_puts<P>(planeA + LP + tx, planeB + LP + tx, tx, tpi, acc);
       __syncthreads();
       float2 cols[4 * (2 * NB + 1)];               // columns x0 - 4 NB .. x0 + 4 NB + 3; own from registers
 #pragma unroll

@@ -68,7 +68,9 @@ def _gpu_worker(rank, world, port, q):
     from favae_b200 import VectorQuantize
     os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
     torch.cuda.set_device(rank)
-    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    import datetime
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank),
+                            timeout=datetime.timedelta(seconds=120))
     try:
         g = np.load(GOLDEN)
         K, D = int(g['K']), int(g['D'])
@@ -106,6 +108,6 @@ def test_sync_codebook_nccl_world2():
     port = _free_port()
     procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
     [p.start() for p in procs]
-    res = dict(q.get(timeout=300) for _ in range(2))
+    res = dict(q.get(timeout=200) for _ in range(2))
     [p.join(timeout=60) for p in procs]
     assert res == {0: True, 1: True}
