@@ -662,10 +662,16 @@ def main():
         os._exit(1 if failed else 0)
 
 
-# ncu --set full captures of this round (profiles/ncu_r2_summary.md): dram__bytes_read+write per element
-NCU_TRAFFIC = {'blur_backward': (12.0, 'ncu --set full, blur_adjsig_kernel<9,64>: 562.0 MB read + 242.2 MB written '
-                                       'for 1024 maps of 256^2 = 12.0 B/element (profiles/ncu_r1_summary.md)'),
-               'ffl2': (15.48, 'ncu --set full, ffl_kernel<256>: 15.48 B/element (profiles/ncu_r1_summary.md)')}
+# ncu --set full captures of this round (profiles/ncu_r2_summary.md): dram__bytes_read + write per element
+NCU_TRAFFIC = {
+    'blur_backward': (12.00, 'ncu --set full, blur_adjsig_kernel<9,64>: 561.9 MB read + 242.9 MB written for 1024 maps '
+                             'of 256^2 = 12.00 B/element (profiles/ncu_r2_blur_bwd_raw.csv)'),
+    'blur_diff': (12.27, 'ncu --set full, blur_diff_kernel<9,64>: 586.5 MB read + 236.9 MB written for 1024 maps of '
+                         '256^2 = 12.27 B/element (profiles/ncu_r2_blur_diff_raw.csv)'),
+    'ffl_diff': (7.12, 'ncu --set full, ffl_kernel<256> single-input form: 268.5 MB read + 209.1 MB written for 1024 maps '
+                       'of 256^2 = 7.12 B/element, part of the last gradient stores still in L2 when the kernel ends '
+                       '(profiles/ncu_r2_ffldiff_raw.csv)'),
+    'ffl2': (15.48, 'ncu --set full, ffl_kernel<256> two-input form: 15.48 B/element (profiles/ncu_r1_summary.md)')}
 
 
 def kernel_groups(trace, wl, args, pk, steps):
@@ -692,14 +698,20 @@ def kernel_groups(trace, wl, args, pk, steps):
     l0_two = [ms for ms, a in ffl if a[2] == maps_l0 and a[3] == h0 and a[1] is not None]
     g = add('ffl_level0_difference', f'ffl_kernel<{h0}> on the level-0 difference map: read d, write G in place '
             '(8 B/element)', l0_diff, 8.0 * e_l0)
+    if g and h0 == 256:
+        g['traffic'] = NCU_TRAFFIC['ffl_diff'][0] * e_l0
+        g['traffic_source'] = NCU_TRAFFIC['ffl_diff'][1]
     g = add('ffl_level0_two_inputs', f'ffl_kernel<{h0}> (level-0 spectrum loss, read pred/target, write both '
             'gradients: 16 B/element)', l0_two, 16.0 * e_l0)
     if g:
         g['traffic'] = 15.48 * e_l0
         g['traffic_source'] = NCU_TRAFFIC['ffl2'][1]
     bd = [ms for ms, a in trace.get('favae_blur_diff_forward', []) if a[2] == maps_l0 and a[3] == h0]
-    add('blur_difference_level0', f'blur_diff_kernel<{wl["ksize"]},32>: d = B(dec) - B(enc), read enc/dec, write d '
-        '(12 B/element)', bd, 12.0 * e_l0)
+    g = add('blur_difference_level0', f'blur_diff_kernel<{wl["ksize"]},64>: d = B(dec) - B(enc), read enc/dec, write d '
+            '(12 B/element)', bd, 12.0 * e_l0)
+    if g and wl['ksize'] == 9:
+        g['traffic'] = NCU_TRAFFIC['blur_diff'][0] * e_l0
+        g['traffic_source'] = NCU_TRAFFIC['blur_diff'][1]
     # favae_blur_backward(gy, x, maps, h, w, ks, sigma, scale, gx, gsigma, partials, stream)
     bb = [ms for ms, a in trace.get('favae_blur_backward', []) if a[2] == maps_l0 and a[3] == h0]
     g = add('blur_adjoint_sigma_level0', f'blur_adjsig_kernel<{wl["ksize"]},64>: adjoint + sigma gradient, read G and x, '
@@ -785,29 +797,32 @@ def microbench(device):
                          'frac_roofline': max(hbm_ms, tc_ms) / ms, 'cpu_ms': cpu_ms, 'cpu_rows_timed': ns})
             print(f'{K:6d} {N:7d} {ms:9.4f} {tf:9.1f} {tf / pk["tf"]:14.3f} {max(hbm_ms, tc_ms) / ms:11.3f} {cpu_ms:10.2f} '
                   f'{cpu_ms / ms:9.0f}  {ns} rows' + (' (scaled)' if ns < N else ''))
-    print('# spectrum loss: FocalFrequencyLoss forward + both gradients (16 B/element), one fused kernel')
+    print('# spectrum loss: favae_ffl_forward, loss + both gradients (16 B/element), one fused kernel per call (C ABI, CUDA events)')
     print(f'{"B":>3} {"C":>4} {"H":>4} {"ms":>9} {"GB/s":>8} {"of HBM peak":>11} {"cpu ms":>10} {"gpu/cpu":>9}  cpu sample')
-    ffl = favae_b200.FocalFrequencyLoss(loss_weight=0.01)
+    from favae_b200 import _lib
     for (C, H) in ((128, 64), (128, 128), (128, 256), (32, 512), (3, 256), (512, 16), (512, 64)):
         for B in (1, 8, 32):
             if B * C * H * H * 4 > 3 << 30:
                 continue
-            p = torch.randn(B, C, H, H, device=device, requires_grad=True)
-            t = torch.randn(B, C, H, H, device=device, requires_grad=True)
+            p = torch.randn(B, C, H, H, device=device)
+            t = torch.randn(B, C, H, H, device=device)
+            gp, gt = torch.empty_like(p), torch.empty_like(t)
+            ml = torch.empty(B * C, device=device)
+            gs = 2 * 0.01 / p.numel()
 
             def run():
-                p.grad = None; t.grad = None
-                ffl(p, t).backward()
+                _lib.call('favae_ffl_forward', p.data_ptr(), t.data_ptr(), B * C, H, H, 1.0, 0, gs, ml.data_ptr(),
+                          gp.data_ptr(), gt.data_ptr(), None, None, _lib.stream())
             for _ in range(5):
                 run()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             a.record()
-            for _ in range(10):
+            for _ in range(20):
                 run()
             b.record()
             torch.cuda.synchronize()
-            ms = a.elapsed_time(b) / 10
+            ms = a.elapsed_time(b) / 20
             gbs = 16.0 * B * C * H * H / (ms * 1e-3) / 1e9
             cpu_ms = None
             sample = ''
@@ -822,7 +837,7 @@ def microbench(device):
                          'cpu_ms': cpu_ms})
             print(f'{B:3d} {C:4d} {H:4d} {ms:9.4f} {gbs:8.0f} {gbs / pk["hbm"]:11.3f} '
                   + (f'{cpu_ms:10.1f} {cpu_ms / ms:9.0f}  {sample}' if cpu_ms is not None else f'{"-":>10} {"-":>9}'))
-            del p, t
+            del p, t, gp, gt
     print(json.dumps({'microbench': rows}))
 
 

@@ -39,6 +39,8 @@ SIGNATURES = {
     'favae_vq_gather_rows': (_i32, [_vp, _vp, _i64, _i64, _i32, _i64, _vp, _vp]),
     'favae_ffl_supported': (_i32, [_i32, _i32]),
     'favae_ffl_forward': (_i32, [_vp, _vp, _i64, _i32, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'favae_ffl_generic_workspace_bytes': (_sz, [_i64, _i32, _i32]),
+    'favae_ffl_forward_generic': (_i32, [_vp, _vp, _i64, _i32, _i32, _f32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'favae_sum_scaled': (_i32, [_vp, _i64, _f64, _vp, _vp]),
     'favae_scale_inplace': (_i32, [_vp, _vp, _i64, _vp, _vp]),
     'favae_blur_forward': (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),

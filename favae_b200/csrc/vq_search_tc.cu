@@ -489,7 +489,6 @@ constexpr int RESCORE_CAP = 96;      // candidate codes per latent handled in pl
 __global__ void __launch_bounds__(256)
 vq_rescore_kernel(const Params p, const float* __restrict__ xn, const float* __restrict__ en,
                   long long* __restrict__ idx, int* __restrict__ ovf_count, int* __restrict__ ovf_rows) {
-  __shared__ float xs[8][MAX_KB * BK];
   __shared__ unsigned int cand[8][RESCORE_CAP];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
@@ -548,29 +547,50 @@ vq_rescore_kernel(const Params p, const float* __restrict__ xn, const float* __r
     if (lane == 0) idx[row] = (long long)cand[wib][0];
     return;
   }
-  for (int c = lane; c < p.d; c += 32) xs[wib][c] = xn[row * p.d + c];
-  __syncwarp();
-  // each lane scores one candidate: exact fp32, sequential over d (the order of the exact kernel)
-  unsigned long long best = 0ull;
-  for (int i = lane; i < total; i += 32) {
-    const unsigned int code = cand[wib][i];
-    const float4* ev = reinterpret_cast<const float4*>(en + (long long)code * p.d);
-    float acc = 0.f;
-#pragma unroll 4
-    for (int c4 = 0; c4 < p.d / 4; ++c4) {
-      const float4 w = ev[c4];
-      acc = fmaf(xs[wib][4 * c4 + 0], w.x, acc);
-      acc = fmaf(xs[wib][4 * c4 + 1], w.y, acc);
-      acc = fmaf(xs[wib][4 * c4 + 2], w.z, acc);
-      acc = fmaf(xs[wib][4 * c4 + 3], w.w, acc);
-    }
-    const unsigned long long key = ((unsigned long long)f_order(acc) << 32) | (0xFFFFFFFFu - code);
-    best = key > best ? key : best;
-  }
+  // Exact fp32 re-score, the whole warp on one candidate: lane l owns the float4 columns l, l + 32 of
+  // the latent (registers) and of the code row (one coalesced 512-byte request per 128 columns), adds
+  // its products in ascending column order and the 32 partial sums go through one fixed xor-shuffle
+  // tree -- one accumulation order for every candidate, so identical codes still tie exactly and the
+  // lowest index wins.  Four candidates are in flight at a time.  (First version: one lane per
+  // candidate walking its whole row, i.e. 2-3 active lanes chasing 64 dependent 16-byte loads each:
+  // latency bound, 212 us of the 1.55 ms search at N = 262144.)
+  constexpr int XV = MAX_KB * BK / 128;                 // float4 per lane: 2 at d = 256
+  const int nv = p.d >> 2;
+  float4 xv[XV];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-    best = other > best ? other : best;
+  for (int j = 0; j < XV; ++j) {
+    const int c4 = lane + 32 * j;
+    xv[j] = c4 < nv ? reinterpret_cast<const float4*>(xn + row * p.d)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  unsigned long long best = 0ull;
+  for (int i0 = 0; i0 < total; i0 += 4) {
+    float4 ev[4][XV];
+    unsigned int codes[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      codes[q] = cand[wib][min(i0 + q, total - 1)];
+      const float4* er = reinterpret_cast<const float4*>(en + (long long)codes[q] * p.d);
+#pragma unroll
+      for (int j = 0; j < XV; ++j) {
+        const int c4 = lane + 32 * j;
+        ev[q][j] = c4 < nv ? er[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < XV; ++j) {
+        acc = fmaf(xv[j].x, ev[q][j].x, acc);
+        acc = fmaf(xv[j].y, ev[q][j].y, acc);
+        acc = fmaf(xv[j].z, ev[q][j].z, acc);
+        acc = fmaf(xv[j].w, ev[q][j].w, acc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const unsigned long long key = ((unsigned long long)f_order(acc) << 32) | (0xFFFFFFFFu - codes[q]);
+      best = key > best ? key : best;            // a candidate repeated past the end changes nothing
+    }
   }
   if (lane == 0) idx[row] = (long long)(0xFFFFFFFFu - (unsigned int)(best & 0xFFFFFFFFull));
 }

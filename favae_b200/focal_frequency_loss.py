@@ -50,18 +50,30 @@ def _run_ffl(pred, target, loss_weight, alpha, log_matrix, batch_matrix, mean_co
     dev = pred.device
     map_loss = torch.empty((max(maps, 1),), device=dev, dtype=torch.float32)
     st = _lib.stream()
+    lib = _lib.load()
+    if lib.favae_ffl_supported(h, w):
+        def run(gs, ml, a, b, mmax, fmax):
+            _lib.call('favae_ffl_forward', _lib.ptr(pred), _lib.ptr(target), maps, h, w, alpha, int(log_matrix),
+                      gs, _lib.ptr(ml), _lib.ptr(a), _lib.ptr(b), _lib.ptr(mmax), _lib.ptr(fmax), st)
+    else:
+        # any other H x W (the reference's fft2 takes any size): the direct-DFT kernels of ffl_generic.cu
+        ws_bytes = lib.favae_ffl_generic_workspace_bytes(maps, h, w)
+        if ws_bytes == 0 and maps > 0:
+            raise NotImplementedError(f'favae_b200: spectrum-loss maps larger than 2048 per side are not supported, '
+                                      f'got {h}x{w}')
+        ws = torch.empty((max(ws_bytes, 16),), device=dev, dtype=torch.uint8)
+
+        def run(gs, ml, a, b, mmax, fmax):
+            _lib.call('favae_ffl_forward_generic', _lib.ptr(pred), _lib.ptr(target), maps, h, w, alpha,
+                      int(log_matrix), gs, _lib.ptr(ml), _lib.ptr(a), _lib.ptr(b), _lib.ptr(mmax), _lib.ptr(fmax),
+                      _lib.ptr(ws), st)
     if batch_matrix:
         map_max = torch.empty((max(maps, 1),), device=dev, dtype=torch.float32)
-        _lib.call('favae_ffl_forward', _lib.ptr(pred), _lib.ptr(target), maps, h, w, alpha,
-                  int(log_matrix), 0.0, _lib.ptr(map_loss), None, None, _lib.ptr(map_max), None, st)
+        run(0.0, map_loss, None, None, map_max, None)
         gmax = map_max[:maps].amax().reshape(1) if maps else torch.ones(1, device=dev)
-        _lib.call('favae_ffl_forward', _lib.ptr(pred), _lib.ptr(target), maps, h, w, alpha,
-                  int(log_matrix), gscale, _lib.ptr(map_loss), _lib.ptr(gp), _lib.ptr(gt), None,
-                  _lib.ptr(gmax), st)
+        run(gscale, map_loss, gp, gt, None, gmax)
     else:
-        _lib.call('favae_ffl_forward', _lib.ptr(pred), _lib.ptr(target), maps, h, w, alpha,
-                  int(log_matrix), gscale, _lib.ptr(map_loss), _lib.ptr(gp), _lib.ptr(gt), None,
-                  None, st)
+        run(gscale, map_loss, gp, gt, None, None)
     loss = torch.empty((1,), device=dev, dtype=torch.float32)
     _lib.call('favae_sum_scaled', _lib.ptr(map_loss), maps, loss_weight / mean_count, _lib.ptr(loss), st)
     return loss, gp, gt
@@ -152,10 +164,6 @@ class FocalFrequencyLoss(nn.Module):
         if self.ave_spectrum:
             # the FFT is linear: the mean spectrum is the spectrum of the batch mean
             p, t = p.mean(0, keepdim=True), t.mean(0, keepdim=True)
-        h, w = p.shape[-2:]
-        if not _lib.load().favae_ffl_supported(h, w):
-            raise NotImplementedError(f'favae_b200: spectrum loss needs square power-of-two maps with side '
-                                      f'in [8, 512], got {h}x{w}')
         p, t = p.contiguous(), t.contiguous()
         if p.data_ptr() % 16:            # float4 access in the kernel
             p = p.clone()

@@ -136,6 +136,17 @@ int favae_ffl_forward(const float* pred, const float* target, int64_t maps, int 
                       float* grad_pred, float* grad_target, float* map_max,
                       const float* fmax_override, void* stream);
 
+/* The same contract for ANY map size 1 <= h, w <= 2048 (the reference's torch.fft.fft2 takes any
+ * size): direct separable DFT passes through a caller-provided workspace of
+ * favae_ffl_generic_workspace_bytes(maps, h, w) bytes (maps are processed in chunks of at most
+ * 256 MB of spectrum).  Cold path: O(h w (h + w)) multiply-adds per map; every FA-VAE
+ * configuration produces power-of-two squares, which take favae_ffl_forward. */
+size_t favae_ffl_generic_workspace_bytes(int64_t maps, int h, int w);
+int favae_ffl_forward_generic(const float* pred, const float* target, int64_t maps, int h, int w,
+                              float alpha, int log_matrix, float grad_scale, float* map_loss,
+                              float* grad_pred, float* grad_target, float* map_max,
+                              const float* fmax_override, void* workspace, void* stream);
+
 /* out[0] = scale * sum(v[0..n)) accumulated in fp64, deterministic. */
 int favae_sum_scaled(const float* v, int64_t n, double scale, float* out, void* stream);
 
