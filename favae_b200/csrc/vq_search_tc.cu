@@ -488,7 +488,8 @@ constexpr int RESCORE_CAP = 96;      // candidate codes per latent handled in pl
 
 __global__ void __launch_bounds__(256)
 vq_rescore_kernel(const Params p, const float* __restrict__ xn, const float* __restrict__ en,
-                  long long* __restrict__ idx, int* __restrict__ ovf_count, int* __restrict__ ovf_rows) {
+                  long long* __restrict__ idx, int* __restrict__ ovf_count, int* __restrict__ ovf_rows,
+                  unsigned long long* __restrict__ keys) {
   __shared__ unsigned int cand[8][RESCORE_CAP];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + wib;
@@ -500,6 +501,22 @@ vq_rescore_kernel(const Params p, const float* __restrict__ xn, const float* __r
   const long long c1 = ((long long)(mu + 1) * p.code_tiles - 1) / p.per_cta;
   const int nrec = (int)(c1 - c0 + 1) * 2;
   const long long base = row * p.slots * 2;
+  // Everything the first 32 candidate entries need is requested BEFORE the running maximum is known
+  // (entries past a record's count hold stale values; the predicate below discards them): one global
+  // round trip per latent instead of a chain of four dependent ones (max -> count -> value -> chunk /
+  // mask), which was what this warp-per-latent kernel spent its time on -- most latents end with a
+  // single candidate and never reach the dot products.
+  const int nent = nrec * CAP;
+  const long long ebase = base * CAP;
+  float pv = 0.f;
+  unsigned int pchunk = 0, pmask = 0;
+  int pcnt = 0;
+  if (lane < nent) {
+    pv = p.ws_val[ebase + lane];
+    pchunk = p.ws_idx[ebase + lane];
+    pmask = p.ws_mask[ebase + lane];
+    pcnt = p.ws_cnt[base + lane / CAP];
+  }
   float gmax = -INFINITY;
   bool ovf = false;
   for (int s = lane; s < nrec; s += 32) {
@@ -511,15 +528,16 @@ vq_rescore_kernel(const Params p, const float* __restrict__ xn, const float* __r
   const float thr = gmax - TAU;
   // gather the candidate codes of all records still inside the band
   int total = 0;
-  const int nent = nrec * CAP;
   for (int e0 = 0; e0 < nent && !ovf; e0 += 32) {
     const int e = e0 + lane;
     unsigned int chunk = 0, mask = 0;
-    if (e < nent) {
+    if (e0 == 0) {
+      if (lane < nent && (lane % CAP) < pcnt && pv >= thr) { chunk = pchunk; mask = pmask; }
+    } else if (e < nent) {
       const int s = e / CAP, i = e % CAP;
-      if (i < p.ws_cnt[base + s] && p.ws_val[(base + s) * CAP + i] >= thr) {
-        chunk = p.ws_idx[(base + s) * CAP + i];
-        mask = p.ws_mask[(base + s) * CAP + i];
+      if (i < p.ws_cnt[base + s] && p.ws_val[ebase + e] >= thr) {
+        chunk = p.ws_idx[ebase + e];
+        mask = p.ws_mask[ebase + e];
       }
     }
     const int mine = __popc(mask);
@@ -539,7 +557,10 @@ vq_rescore_kernel(const Params p, const float* __restrict__ xn, const float* __r
     }
   }
   if (ovf) {
-    if (lane == 0) ovf_rows[atomicAdd(ovf_count, 1)] = (int)row;
+    if (lane == 0) {
+      keys[row] = 0ull;                          // meeting point of the fallback kernel's code slices
+      ovf_rows[atomicAdd(ovf_count, 1)] = (int)row;
+    }
     return;
   }
   __syncwarp();
@@ -595,44 +616,80 @@ vq_rescore_kernel(const Params p, const float* __restrict__ xn, const float* __r
   if (lane == 0) idx[row] = (long long)(0xFFFFFFFFu - (unsigned int)(best & 0xFFFFFFFFull));
 }
 
-// exhaustive fp32 search of the (rare) rows whose candidate list overflowed: one block per row
+// Exhaustive fp32 search of the (rare) rows whose candidate list overflowed.  A work unit is (row, slice
+// of the codebook), with enough slices that a single overflowing latent still uses the whole GPU (one
+// block per row took 1 ms for one row at K = 16384: every thread walked 64 code rows with 16-byte
+// strided loads).  Within a unit each warp scores one code at a time with the accumulation order of
+// vq_rescore_kernel (so ties between identical codes stay exact), the slices meet in a 64-bit
+// atomicMax on keys[row] (zeroed by the re-score kernel when it queued the row), and the block that
+// finishes the last unit decodes the winners.
 __global__ void __launch_bounds__(256)
 vq_fallback_kernel(const Params p, const float* __restrict__ xn, const float* __restrict__ en,
-                   long long* __restrict__ idx, const int* __restrict__ ovf_count,
-                   const int* __restrict__ ovf_rows) {
+                   long long* __restrict__ idx, int* __restrict__ ovf_count, const int* __restrict__ ovf_rows,
+                   unsigned long long* __restrict__ keys) {
   __shared__ unsigned long long wbest[8];
+  __shared__ int last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int count = *ovf_count;
-  for (int i = blockIdx.x; i < count; i += gridDim.x) {
-    const long long row = ovf_rows[i];
-    const float* x = xn + row * p.d;
+  const int count = ovf_count[0];
+  if (count == 0) return;
+  int slices = (int)gridDim.x / count;
+  slices = slices < 1 ? 1 : (slices > 64 ? 64 : slices);
+  const long long per = (p.k + slices - 1) / slices;
+  const long long units = (long long)count * slices;
+  constexpr int XV = MAX_KB * BK / 128;
+  const int nv = p.d >> 2;
+  int done = 0;
+  for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    const long long row = ovf_rows[u / slices];
+    const long long c0 = (u % slices) * per, c1 = c0 + per < p.k ? c0 + per : p.k;
+    float4 xv[XV];
+#pragma unroll
+    for (int j = 0; j < XV; ++j) {
+      const int c4 = lane + 32 * j;
+      xv[j] = c4 < nv ? reinterpret_cast<const float4*>(xn + row * p.d)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     unsigned long long best = 0ull;
-    for (long long code = threadIdx.x; code < p.k; code += 256) {
-      const float4* ev = reinterpret_cast<const float4*>(en + code * p.d);
+    for (long long code = c0 + warp; code < c1; code += 8) {
+      const float4* er = reinterpret_cast<const float4*>(en + code * p.d);
       float acc = 0.f;
-      for (int c4 = 0; c4 < p.d / 4; ++c4) {
-        const float4 w = ev[c4];
-        acc = fmaf(x[4 * c4 + 0], w.x, acc);
-        acc = fmaf(x[4 * c4 + 1], w.y, acc);
-        acc = fmaf(x[4 * c4 + 2], w.z, acc);
-        acc = fmaf(x[4 * c4 + 3], w.w, acc);
+#pragma unroll
+      for (int j = 0; j < XV; ++j) {
+        const int c4 = lane + 32 * j;
+        const float4 w = c4 < nv ? er[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc = fmaf(xv[j].x, w.x, acc);
+        acc = fmaf(xv[j].y, w.y, acc);
+        acc = fmaf(xv[j].z, w.z, acc);
+        acc = fmaf(xv[j].w, w.w, acc);
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       const unsigned long long key = ((unsigned long long)f_order(acc) << 32) | (0xFFFFFFFFu - (unsigned int)code);
       best = key > best ? key : best;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-      best = other > best ? other : best;
     }
     if (lane == 0) wbest[warp] = best;
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long b = 0ull;
       for (int w = 0; w < 8; ++w) b = wbest[w] > b ? wbest[w] : b;
-      idx[row] = (long long)(0xFFFFFFFFu - (unsigned int)(b & 0xFFFFFFFFull));
+      atomicMax(&keys[row], b);
     }
     __syncthreads();
+    ++done;
+  }
+  // the block that completes the last unit decodes every overflow row
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const long long before = atomicAdd(reinterpret_cast<unsigned long long*>(ovf_count + 2), (unsigned long long)done);
+    last = (before + done == units) ? 1 : 0;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    for (int i = threadIdx.x; i < count; i += 256) {
+      const long long row = ovf_rows[i];
+      const unsigned long long b = *reinterpret_cast<volatile unsigned long long*>(&keys[row]);
+      idx[row] = (long long)(0xFFFFFFFFu - (unsigned int)(b & 0xFFFFFFFFull));
+    }
   }
 }
 
@@ -754,8 +811,7 @@ int favae_vq_search_tc_overflow_rows(const void* workspace, int64_t n, int64_t k
 int favae_vq_search_tc(const void* xh, const void* eh, const float* xn, const float* en, int64_t n,
                        int64_t k, int d, void* workspace, size_t workspace_bytes, uint64_t* keys,
                        int64_t* idx, void* stream) {
-  (void)keys;
-  FAVAE_REQUIRE(xh && eh && xn && en && idx && workspace, "vq_search_tc: null pointer");
+  FAVAE_REQUIRE(xh && eh && xn && en && idx && workspace && keys, "vq_search_tc: null pointer");
   FAVAE_REQUIRE(n > 0 && favae_vq_search_tc_workspace_bytes(n, k, d) > 0,
                 "vq_search_tc: needs d % 64 == 0, d <= 256, k % 256 == 0");
   const tc::Plan pl = tc::make_plan(n, k);
@@ -814,10 +870,12 @@ int favae_vq_search_tc(const void* xh, const void* eh, const float* xn, const fl
   }
   rc = check_launch("vq_search_tc");
   if (rc) return rc;
-  tc::vq_rescore_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(p, xn, en, (long long*)idx, ovf_count, ovf_rows);
+  tc::vq_rescore_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(p, xn, en, (long long*)idx, ovf_count, ovf_rows,
+                                                                 (unsigned long long*)keys);
   rc = check_launch("vq_rescore");
   if (rc) return rc;
-  tc::vq_fallback_kernel<<<num_sms(), 256, 0, s>>>(p, xn, en, (long long*)idx, ovf_count, ovf_rows);
+  tc::vq_fallback_kernel<<<num_sms() * 2, 256, 0, s>>>(p, xn, en, (long long*)idx, ovf_count, ovf_rows,
+                                                       (unsigned long long*)keys);
   return check_launch("vq_fallback");
 }
 }

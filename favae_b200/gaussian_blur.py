@@ -166,7 +166,12 @@ def lazy_gaussian_blur(x, sigma, kernel_size):
 
 def _blur_method(self, x, i, device=None):
     """Signature of the reference ``_gaussian_blur(self, x, i[, device])``.  Returns the deferred
-    handle: the only consumer in the reference is the DSL loss wrapper."""
+    handle: the only consumer in the reference is the DSL loss wrapper.  ``FAVAE_LAZY_BLUR=0`` selects
+    the eager op instead (needed under DDP with ``find_unused_parameters=True``, which walks the
+    autograd graph of the module outputs and cannot see through a handle)."""
+    import os
+    if os.environ.get('FAVAE_LAZY_BLUR', '1') in ('', '0'):
+        return gaussian_blur_reflect(x, self.sigmas[i], self.kernel_size)
     return lazy_gaussian_blur(x, self.sigmas[i], self.kernel_size)
 
 

@@ -297,6 +297,25 @@ def test_tensor_core_search_ties_duplicates_and_overflow():
     _assert_indices(o['tc'], o['exact'], x, embed)
 
 
+def test_fallback_search_single_and_many_overflow_rows():
+    """The exhaustive fallback splits the codebook into slices across blocks (one overflowing latent must
+    not serialise on one block) and meets in a 64-bit atomicMax: one, a few and many overflow rows."""
+    torch.manual_seed(9)
+    k, d = 16384, 256
+    embed = torch.nn.functional.normalize(torch.randn(k, d, device='cuda'), dim=-1)
+    embed[9000:9200] = embed[4242].clone()           # 201 identical codes: any latent near them overflows
+    for n_over in (1, 5, 700):
+        x = torch.randn(1024, d, device='cuda')
+        rows = torch.randperm(1024)[:n_over]
+        x[rows] = embed[4242] * 1.7 + 1e-5 * torch.randn(n_over, d, device='cuda')
+        x[rows[0]] = 0.0                             # all-zero latent: every code ties -> index 0
+        o = _tc_search(x, embed)
+        assert o['tc'][rows[0]].item() == 0
+        if n_over > 1:
+            assert torch.all(o['tc'][rows[1:]] == 4242)
+        _assert_indices(o['tc'], o['exact'], x, embed)
+
+
 def _big_codebook(g):
     """Seeded initial codebook of a vq_big_* fixture (see tests/test_oracle_vq.py::big_case_codebook)."""
     torch.manual_seed(int(g['seed']))
