@@ -90,7 +90,8 @@ template <int KS, int TH, int MODE>
 __global__ void __launch_bounds__(THREADS, MODE == MODE_ADJ ? FAVAE_ADJ_MINB : FAVAE_FWD_MINB)
 blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ /*aux*/, int h, int w, long long items,
                  int strips, const float* __restrict__ sigma, float* __restrict__ dst,
-                 float* __restrict__ /*partials*/, float oscale) {
+                 float* __restrict__ /*partials*/, float oscale, const float* __restrict__ oscale_dev) {
+  if (oscale_dev) oscale *= oscale_dev[0];       // upstream gradient of the fused DSL level (device scalar)
   // src: x (FWD) or gy (ADJ); dst: y / gx
   static_assert(MODE == MODE_FWD || MODE == MODE_ADJ, "sigma-gradient modes have their own kernels");
   constexpr int P = KS / 2;
@@ -383,7 +384,8 @@ template <int KS, int TH>
 __global__ void __launch_bounds__(THREADS, FAVAE_ADJSIG_MINB)
 blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux, int h, int w, long long items,
                    int strips, const float* __restrict__ sigma, float* __restrict__ dst,
-                   float* __restrict__ partials, float oscale) {
+                   float* __restrict__ partials, float oscale, const float* __restrict__ oscale_dev) {
+  if (oscale_dev) oscale *= oscale_dev[0];       // upstream gradient of the fused DSL level (device scalar)
   // oscale multiplies gx and the sigma partials (the fused DSL op feeds +G to the decoder side and -G
   // to the encoder side, vqgan_losses.py:25: ffl(de, en)); it rides on the D row scaling
   constexpr int P = KS / 2;
@@ -768,18 +770,18 @@ inline long long num_blocks(long long maps, int h, int w, int mode = MODE_FWD) {
 
 template <int KS, int TH, int MODE>
 static int launch_one(const float* src, const float* aux, long long maps, int h, int w, const float* sigma,
-                      float* dst, float* partials, cudaStream_t s, float oscale) {
+                      float* dst, float* partials, cudaStream_t s, float oscale, const float* oscale_dev) {
   const int strips = (h + TH - 1) / TH, groups = THREADS / (w / 4);
   const long long items = maps * strips;
   const long long blocks = (items + groups - 1) / groups;
   const size_t smem = sizeof(float) * 2 * groups * ((MODE == MODE_ADJ_SIG || MODE == MODE_SIGMA) ? 2 : 1) * (size_t)(w + 2 * LPAD);
   if constexpr (MODE == MODE_ADJ_SIG)
-    blur_adjsig_kernel<KS, TH><<<(unsigned)blocks, THREADS, smem, s>>>(src, aux, h, w, items, strips, sigma, dst, partials, oscale);
+    blur_adjsig_kernel<KS, TH><<<(unsigned)blocks, THREADS, smem, s>>>(src, aux, h, w, items, strips, sigma, dst, partials, oscale, oscale_dev);
   else if constexpr (MODE == MODE_SIGMA)
     blur_sigma_kernel<KS, TH><<<(unsigned)blocks, THREADS, smem, s>>>(src, aux, h, w, items, strips, sigma, partials);
   else
     blur_fast_kernel<KS, TH, MODE><<<(unsigned)blocks, THREADS, smem, s>>>(src, aux, h, w, items, strips, sigma, dst,
-                                                                        partials, oscale);
+                                                                        partials, oscale, oscale_dev);
   return check_launch("blur_fast");
 }
 
@@ -813,17 +815,17 @@ static int launch_diff(const float* enc, const float* dec, long long maps, int h
 
 template <int MODE>
 static int launch(const float* src, const float* aux, long long maps, int h, int w, int ks, const float* sigma,
-                  float* dst, float* partials, cudaStream_t s, float oscale = 1.0f) {
+                  float* dst, float* partials, cudaStream_t s, float oscale = 1.0f, const float* oscale_dev = nullptr) {
 #define FAVAE_BLUR_CASE(KS)                                                                         \
   case KS:                                                                                          \
     if (MODE == MODE_ADJ_SIG && strip_rows(h, MODE) == FAVAE_ADJSIG_TH)                             \
-      return launch_one<KS, (MODE == MODE_ADJ_SIG ? FAVAE_ADJSIG_TH : 32), MODE>(src, aux, maps, h, w, sigma, dst, partials, s, oscale); \
+      return launch_one<KS, (MODE == MODE_ADJ_SIG ? FAVAE_ADJSIG_TH : 32), MODE>(src, aux, maps, h, w, sigma, dst, partials, s, oscale, oscale_dev); \
     if (MODE == MODE_FWD && FAVAE_FWD_TH > 32 && strip_rows(h, MODE) == FAVAE_FWD_TH)               \
-      return launch_one<KS, (MODE == MODE_FWD ? FAVAE_FWD_TH : 32), MODE>(src, aux, maps, h, w, sigma, dst, partials, s, oscale); \
+      return launch_one<KS, (MODE == MODE_FWD ? FAVAE_FWD_TH : 32), MODE>(src, aux, maps, h, w, sigma, dst, partials, s, oscale, oscale_dev); \
     if (MODE == MODE_ADJ && strip_rows(h, MODE) == FAVAE_ADJ_TH)                                    \
-      return launch_one<KS, (MODE == MODE_ADJ ? FAVAE_ADJ_TH : 32), MODE>(src, aux, maps, h, w, sigma, dst, partials, s, oscale); \
-    return strip_rows(h, MODE) == 16 ? launch_one<KS, 16, MODE>(src, aux, maps, h, w, sigma, dst, partials, s, oscale) \
-                                     : launch_one<KS, 32, MODE>(src, aux, maps, h, w, sigma, dst, partials, s, oscale);
+      return launch_one<KS, (MODE == MODE_ADJ ? FAVAE_ADJ_TH : 32), MODE>(src, aux, maps, h, w, sigma, dst, partials, s, oscale, oscale_dev); \
+    return strip_rows(h, MODE) == 16 ? launch_one<KS, 16, MODE>(src, aux, maps, h, w, sigma, dst, partials, s, oscale, oscale_dev) \
+                                     : launch_one<KS, 32, MODE>(src, aux, maps, h, w, sigma, dst, partials, s, oscale, oscale_dev);
   switch (ks) {
     FAVAE_BLUR_CASE(3)
     FAVAE_BLUR_CASE(5)

@@ -262,8 +262,8 @@ int favae_blur_diff_forward(const float* enc, const float* dec, int64_t maps, in
 }
 
 int favae_blur_backward(const float* gy, const float* x, int64_t maps, int h, int w, int ksize,
-                        const float* sigma, float out_scale, float* gx, float* gsigma, float* partials,
-                        void* stream) {
+                        const float* sigma, float out_scale, const float* out_scale_dev, float* gx, float* gsigma,
+                        float* partials, void* stream) {
   FAVAE_REQUIRE(gy && sigma && (gx || gsigma), "blur_backward: null pointer");
   FAVAE_REQUIRE(!gsigma || (x && partials), "blur_backward: sigma gradient needs x and partials");
   int rc = blur_check(maps, h, w, ksize);
@@ -274,15 +274,16 @@ int favae_blur_backward(const float* gy, const float* x, int64_t maps, int h, in
     return 0;
   }
   if (gx && blurf::supported(h, w, ksize) && aligned16(gy) && aligned16(gx) && (!gsigma || aligned16(x))) {
-    if (!gsigma) return blurf::launch<blurf::MODE_ADJ>(gy, nullptr, maps, h, w, ksize, sigma, gx, nullptr, s, out_scale);
+    if (!gsigma) return blurf::launch<blurf::MODE_ADJ>(gy, nullptr, maps, h, w, ksize, sigma, gx, nullptr, s, out_scale, out_scale_dev);
     // One fused kernel (12 B/element: gy and x read once, gx written).  FAVAE_BLUR_SIGMA=split runs
     // the plain adjoint and the forward-path sigma-gradient kernel instead (16 B/element).  Measured
     // on B200 at 4096 maps of 256^2, k = 9: fused 1.11 ms, split 0.56 + 0.69 ms.
     static const bool split = [] { const char* e = getenv("FAVAE_BLUR_SIGMA"); return e && e[0] == 's'; }();
     if (!split) {
-      rc = blurf::launch<blurf::MODE_ADJ_SIG>(gy, x, maps, h, w, ksize, sigma, gx, partials, s, out_scale);
+      rc = blurf::launch<blurf::MODE_ADJ_SIG>(gy, x, maps, h, w, ksize, sigma, gx, partials, s, out_scale, out_scale_dev);
     } else {
-      rc = blurf::launch<blurf::MODE_ADJ>(gy, nullptr, maps, h, w, ksize, sigma, gx, nullptr, s, out_scale);
+      FAVAE_REQUIRE(!out_scale_dev, "blur_backward: FAVAE_BLUR_SIGMA=split does not take a device-side scale");
+      rc = blurf::launch<blurf::MODE_ADJ>(gy, nullptr, maps, h, w, ksize, sigma, gx, nullptr, s, out_scale, out_scale_dev);
       if (rc) return rc;
       rc = blurf::launch<blurf::MODE_SIGMA>(x, gy, maps, h, w, ksize, sigma, nullptr, partials, s);
     }
@@ -291,7 +292,8 @@ int favae_blur_backward(const float* gy, const float* x, int64_t maps, int h, in
     return favae_sum_scaled(partials, blurf::num_blocks(maps, h, w, split ? blurf::MODE_SIGMA : blurf::MODE_ADJ_SIG),
                             split ? (double)out_scale : 1.0, gsigma, stream);
   }
-  FAVAE_REQUIRE(out_scale == 1.0f, "blur_backward: out_scale != 1 needs the streaming path (favae_blur_fast_supported)");
+  FAVAE_REQUIRE(out_scale == 1.0f && !out_scale_dev,
+                "blur_backward: an output scale needs the streaming path (favae_blur_fast_supported)");
   const unsigned blocks = (unsigned)blur_blocks(maps, h, w);
   if (gx) {
     blur_adjoint_kernel<<<blocks, 256, 0, s>>>(gy, h, w, ksize, sigma, gx);

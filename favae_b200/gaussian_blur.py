@@ -46,9 +46,9 @@ class _BlurFunction(torch.autograd.Function):
         return gx, (gs.reshape(sigma.shape) if gs is not None else None), None
 
 
-def blur_backward(gy, x, sigma, kernel_size, need_x, need_s, out_scale):
-    """(out_scale * blur^T(gy), out_scale * d<gy, blur(x)>/dsigma) through favae_blur_backward; the
-    fused adjoint + sigma-gradient kernel always produces gx."""
+def blur_backward(gy, x, sigma, kernel_size, need_x, need_s, out_scale, scale_dev=None):
+    """(s * blur^T(gy), s * d<gy, blur(x)>/dsigma) with s = out_scale * scale_dev[0] through
+    favae_blur_backward; the fused adjoint + sigma-gradient kernel always produces gx."""
     if not (need_x or need_s):
         return None, None
     h, w = x.shape[-2:]
@@ -61,7 +61,8 @@ def blur_backward(gy, x, sigma, kernel_size, need_x, need_s, out_scale):
             partials = torch.empty((max(int(_lib.load().favae_blur_partials(maps, h, w)), 1),),
                                    device=x.device, dtype=torch.float32)
         _lib.call('favae_blur_backward', _lib.ptr(gy), _lib.ptr(x), maps, h, w, kernel_size, _lib.ptr(sigma),
-                  float(out_scale), _lib.ptr(gx), _lib.ptr(gs), _lib.ptr(partials), _lib.stream())
+                  float(out_scale), _lib.ptr(scale_dev), _lib.ptr(gx), _lib.ptr(gs), _lib.ptr(partials),
+                  _lib.stream())
     return (gx if need_x else None), gs
 
 

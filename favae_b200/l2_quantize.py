@@ -390,7 +390,8 @@ class _CodebookBase(nn.Module):
         idx, en, eh = self._search_rows(xn, xh, None, n)
 
         out = torch.empty_like(x)
-        loss_sum = torch.zeros((1,), device=dev, dtype=torch.float32)
+        # written in full by favae_vq_gather_st when the loss is wanted
+        loss_sum = (torch.empty if want_loss else torch.zeros)((1,), device=dev, dtype=torch.float32)
         blocks = (n + 31) // 32 if hw == 1 else (n // hw) * ((hw + 31) // 32)
         partials = self._buf('partials', (max(blocks, 1),), torch.float32, dev) if want_loss else None
         _lib.call('favae_vq_gather_st', _lib.ptr(x), _lib.ptr(embed), _lib.ptr(idx), n, k, d, hw,
@@ -552,10 +553,11 @@ class VectorQuantize(nn.Module):
             with torch.no_grad():
                 quantize, idx, loss_sum = _QuantizeFunction.apply(x, cb, hw, False, False)
 
-        loss = torch.zeros(1, device=device, requires_grad=training)            # :556
+        if want_loss:
+            loss = loss_sum * (self.commitment_weight / x.numel())               # :556, :560-561 (shape (1,))
+        else:
+            loss = torch.zeros(1, device=device, requires_grad=training)        # :556
         if training:
-            if want_loss:
-                loss = loss + loss_sum * (self.commitment_weight / x.numel())    # :560-561
             if self.orthogonal_reg_weight > 0:                                  # :563-577
                 # Reproduced as written in the reference, quirks included: the (1, K, D) codebook is
                 # indexed and measured along dim 0 (the head axis, size 1).  `num_codes` is therefore 1,

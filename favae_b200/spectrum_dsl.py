@@ -93,17 +93,16 @@ class _DSLFunction(torch.autograd.Function):
         ksize = ctx.cfg[0]
         with _lib.on_device_of(enc, dec, sigma_enc, sigma_dec):
             g = ctx.g
-            if g is None:                        # second backward through the same graph: recompute G
-                _, g = _DSLFunction._difference_and_loss(enc, sigma_enc, dec, sigma_dec, ctx.cfg, True)
-            ctx.g = None
             s = go.detach().to(torch.float32).reshape(1)
             if ctx.cfg[5] != 1.0:
                 s = s / ctx.cfg[5]               # exactly 1.0 when the announced scale was applied
             s = s.contiguous()
-            _lib.call('favae_scale_inplace', _lib.ptr(g), None, g.numel(), _lib.ptr(s), _lib.stream())
+            # the upstream factor (exactly 1 when the announced scale was applied) rides on the adjoint
+            # kernels' output scale: G itself is never re-scaled in HBM.
             # ffl(pred = blur(dec), target = blur(enc)): +G flows to the decoder side, -G to the encoder side
-            g_dec, gs_dec = blur_backward(g, dec, sigma_dec, ksize, ctx.need[2], ctx.need[3], 1.0)
-            g_enc, gs_enc = blur_backward(g, enc, sigma_enc, ksize, ctx.need[0], ctx.need[1], -1.0)
+            g_dec, gs_dec = blur_backward(g, dec, sigma_dec, ksize, ctx.need[2], ctx.need[3], 1.0, s)
+            g_enc, gs_enc = blur_backward(g, enc, sigma_enc, ksize, ctx.need[0], ctx.need[1], -1.0, s)
+            ctx.g = g                            # G is untouched: a second backward can reuse it
         gs_enc = gs_enc.reshape(sigma_enc.shape) if gs_enc is not None else None
         gs_dec = gs_dec.reshape(sigma_dec.shape) if gs_dec is not None else None
         return g_enc, gs_enc, g_dec, gs_dec, None, None, None, None, None

@@ -17,13 +17,20 @@ from .spectrum_dsl import dsl_level_loss, fusable
 __all__ = ['recon_ffl_loss', 'recon_ffl_features_loss', 'recon_sl_gaussian_features_loss']
 
 
+def _mean_of_levels(losses, n, device):
+    """``(zeros(1) + l0 + l1 + ...) / n`` of the reference (:21-28) as stack, sum, divide: three small
+    launches instead of n + 2, same (1,) shape."""
+    if not losses:
+        return torch.zeros(1, device=device)
+    return torch.stack(losses).sum().reshape(1) / n
+
+
 def recon_ffl_loss(ffl, x, x_recon):                                   # :13-14
     return ffl(x_recon, x)
 
 
 def recon_ffl_features_loss(ffl, en_feat, de_feat, device):            # :18-30
     de_feat.reverse()
-    loss = torch.zeros(1, device=device)
     losses = []
     n = len(en_feat)
     # `loss / len` (:28): the float32 factor autograd will hand back, announced to the loss so that its
@@ -34,23 +41,17 @@ def recon_ffl_features_loss(ffl, en_feat, de_feat, device):            # :18-30
                 level = dsl_level_loss(ffl, de_feat[i], en_feat[i])
             else:
                 level = ffl(de_feat[i], en_feat[i])
-            loss = loss + level
             losses.append(level)
-    loss = loss / n
-    return loss, losses
+    return _mean_of_levels(losses, n, device), losses
 
 
 def recon_sl_gaussian_features_loss(ffl, gaussian_kernel, gaussian_sigma, en_feat, de_feat, device):  # :34-50
     de_feat.reverse()
-    loss = torch.zeros(1, device=device)
     losses = []
     n = len(en_feat)
     with expected_upstream_scale(float(torch.tensor(1.0) / n)):
         for i in range(len(en_feat)):
             e = gaussian_blur_reflect(en_feat[i], float(gaussian_sigma), gaussian_kernel)
             d = gaussian_blur_reflect(de_feat[i], float(gaussian_sigma), gaussian_kernel)
-            level = ffl(d, e)
-            loss = loss + level
-            losses.append(level)
-    loss = loss / n
-    return loss, losses
+            losses.append(ffl(d, e))
+    return _mean_of_levels(losses, n, device), losses

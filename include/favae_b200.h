@@ -161,15 +161,18 @@ int favae_scale_inplace(float* a, float* b, int64_t n, const float* s, void* str
  * (losses/vqgan_losses.py:35). */
 int favae_blur_forward(const float* x, int64_t maps, int h, int w, int ksize, const float* sigma,
                        float* y, void* stream);
-/* gx = out_scale * adjoint blur of gy;  gsigma[0] = out_scale * d/dsigma <gy, blur(x)>
- * (nullable; partials = favae_blur_partials(maps,h,w) floats of scratch).  out_scale != 1 (the
- * fused DSL op passes -1 for the encoder side) needs favae_blur_fast_supported(h, w, ksize).
+/* gx = s * adjoint blur of gy;  gsigma[0] = s * d/dsigma <gy, blur(x)> with
+ * s = out_scale * (out_scale_dev ? out_scale_dev[0] : 1)  (gsigma nullable; partials =
+ * favae_blur_partials(maps,h,w) floats of scratch).  s != 1 needs
+ * favae_blur_fast_supported(h, w, ksize): the fused DSL op passes out_scale = -1 for the encoder side
+ * and the upstream gradient of the level as the device scalar, so the gradient map G is never
+ * re-scaled in HBM.
  * Diagnostics only: the environment variable FAVAE_BLUR_SIGMA=split computes the two results
  * with two kernels instead of the fused one. */
 int64_t favae_blur_partials(int64_t maps, int h, int w);
 int favae_blur_backward(const float* gy, const float* x, int64_t maps, int h, int w, int ksize,
-                        const float* sigma, float out_scale, float* gx, float* gsigma,
-                        float* partials, void* stream);
+                        const float* sigma, float out_scale, const float* out_scale_dev, float* gx,
+                        float* gsigma, float* partials, void* stream);
 
 /* 1 when the streaming blur kernels take this shape: w a power of two in [8, 512],
  * ksize in {3,5,9,11,15}, ksize/2 < min(h, w). */

@@ -82,10 +82,10 @@ def main():
         gs = torch.empty(1, device=dev)
         parts = torch.empty(int(_lib.load().favae_blur_partials(B * 128, 256, 256)), device=dev)
         ms = timed(lambda: _lib.call('favae_blur_backward', t.data_ptr(), p.data_ptr(), B * 128, 256, 256, 9,
-                                     sig.data_ptr(), 1.0, gp.data_ptr(), gs.data_ptr(), parts.data_ptr(), st()), it)
+                                     sig.data_ptr(), 1.0, None, gp.data_ptr(), gs.data_ptr(), parts.data_ptr(), st()), it)
         print(f'blur bwd+sigma k9  {ms:8.3f} ms  {12 * E / ms / 1e6:8.1f} GB/s (12 B/elem)')
         ms = timed(lambda: _lib.call('favae_blur_backward', t.data_ptr(), p.data_ptr(), B * 128, 256, 256, 9,
-                                     sig.data_ptr(), 1.0, gp.data_ptr(), None, None, st()), it)
+                                     sig.data_ptr(), 1.0, None, gp.data_ptr(), None, None, st()), it)
         print(f'blur bwd k9        {ms:8.3f} ms  {8 * E / ms / 1e6:8.1f} GB/s (8 B/elem)')
     if want('small'):
         # the three 16 x 16 feature levels of the f=16 model: B*512, B*512, B*256 maps
@@ -99,7 +99,7 @@ def main():
                                          ys.data_ptr(), st()), it)
             print(f'blur16 fwd  maps={maps:6d} {ms * 1e3:8.1f} us')
             ms = timed(lambda: _lib.call('favae_blur_backward', gs_.data_ptr(), xs.data_ptr(), maps, 16, 16, 9,
-                                         sg.data_ptr(), 1.0, ys.data_ptr(), g1.data_ptr(), parts.data_ptr(), st()), it)
+                                         sg.data_ptr(), 1.0, None, ys.data_ptr(), g1.data_ptr(), parts.data_ptr(), st()), it)
             print(f'blur16 bwd+sigma maps={maps:6d} {ms * 1e3:8.1f} us')
             ms = timed(lambda: _lib.call('favae_ffl_forward', xs.data_ptr(), gs_.data_ptr(), maps, 16, 16, 1.0, 0,
                                          1e-3, ml.data_ptr(), gp2.data_ptr(), gt2.data_ptr(), None, None, st()), it)
@@ -118,7 +118,7 @@ def main():
                                          ys.data_ptr(), st()), it)
             print(f'blur64 fwd k{ks}        {ms:8.3f} ms  {8 * E4 / ms / 1e6:8.1f} GB/s (8 B/elem)')
             ms = timed(lambda: _lib.call('favae_blur_backward', gs_.data_ptr(), xs.data_ptr(), maps, 64, 64, ks,
-                                         sg.data_ptr(), 1.0, ys.data_ptr(), g1.data_ptr(), parts.data_ptr(), st()), it)
+                                         sg.data_ptr(), 1.0, None, ys.data_ptr(), g1.data_ptr(), parts.data_ptr(), st()), it)
             print(f'blur64 bwd+sigma k{ks}  {ms:8.3f} ms  {12 * E4 / ms / 1e6:8.1f} GB/s (12 B/elem)')
         ms = timed(lambda: _lib.call('favae_ffl_forward', xs.data_ptr(), gs_.data_ptr(), maps, 64, 64, 1.0, 0,
                                      1e-3, ml.data_ptr(), gp2.data_ptr(), gt2.data_ptr(), None, None, st()), it)
