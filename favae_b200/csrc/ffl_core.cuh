@@ -200,6 +200,12 @@ template <int N_, int C_, int MPC_, int THREADS_> struct FflCfg {
   // I/O staging of a row pair (N float2): elements with (c % 4) < 2 in [0, N/2), the others from
   // IO_B2 on; the 8-slot shift keeps the strided float2 reads of the two halves on different banks
   static constexpr int IO_B2 = N / 2 + 8;
+  // Direct I/O (see FflDirect in ffl_driver.cuh) is possible when the TG lanes of a transform cover whole
+  // 32-byte sectors with 4-byte accesses
+#ifndef FAVAE_FFL_DIRECT_IO
+#define FAVAE_FFL_DIRECT_IO 1
+#endif
+  static constexpr bool DIRECT_IO_OK = (R2 >= 8) && FAVAE_FFL_DIRECT_IO;
   static_assert(R2 == 1 || N + 8 <= R1 * STG_STRIDE, "I/O staging must fit the FFT staging area");
 };
 

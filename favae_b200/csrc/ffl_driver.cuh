@@ -82,14 +82,28 @@ FAVAE_HD void ffl_issue_loads(Env& env, const FflParams& p, long long batch, int
 #ifndef FAVAE_FFL_DIFF_PIPE
 #define FAVAE_FFL_DIFF_PIPE 1
 #endif
+// Direct I/O: every thread reads / writes its FFT-layout elements n = R2 e + t of the two rows straight
+// from / to global memory with 4-byte accesses (the TG lanes of a transform cover 4 TG contiguous bytes
+// per instruction) instead of float4 accesses redistributed through the staging area: the same
+// instruction count, two shared-memory passes fewer on the way in and two on the way out (the kernel
+// is shared-memory-bandwidth bound, profiles/ncu_r2_summary.md) -- but four times the global requests
+// through the same L1 pipe.  Measured on B200, 4096 maps of 256^2: single-input form 1.11 -> 1.06 ms,
+// two-input form 1.29 -> 1.35 ms (twice the loads and stores), loss only 0.72 -> 0.74 ms; 128^2
+// two-input 0.74 -> 0.78 ms; 512^2 two-input 2.15 -> 2.05 ms.  Hence: the single-input form from
+// 256^2 up, and 512^2 always.
+template <class Cfg, bool DIFF> struct FflDirect {
+  static constexpr bool value = Cfg::DIRECT_IO_OK && ((DIFF && Cfg::N >= 256) || Cfg::N >= 512);
+};
 template <class Cfg, bool DIFF> struct FflPipe {
   // the single-input form has the registers to keep the next map's first pass in flight under the last
   // gradient stores of the current one (the two-input form spills at 512 threads, see Cfg::PIPELINE_LOADS)
-  static constexpr bool value = Cfg::PIPELINE_LOADS || (DIFF && Cfg::C == 2 && FAVAE_FFL_DIFF_PIPE);
+  static constexpr bool value =
+      !FflDirect<Cfg, DIFF>::value && (Cfg::PIPELINE_LOADS || (DIFF && Cfg::C == 2 && FAVAE_FFL_DIFF_PIPE));
 };
 template <class Cfg, bool FAST = false, bool DIFF = false, class Env>
 FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long long next_batch = -1) {
   constexpr bool PIPE = FflPipe<Cfg, DIFF>::value;
+  constexpr bool DIRECT = FflDirect<Cfg, DIFF>::value;
   constexpr int N = Cfg::N, R1 = Cfg::R1, TG = Cfg::TG, NG = Cfg::NG, HALF = Cfg::HALF;
   constexpr int C = Cfg::C, MPC = Cfg::MPC, T = Cfg::THREADS, PASSES = Cfg::PASSES;
   constexpr int GPC = HALF / C;                 // row pairs / column groups per CTA and map
@@ -113,6 +127,28 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
   constexpr int V4 = Cfg::IO_V4;
   constexpr int IOB4 = Cfg::IO_B2 / 2;          // float4 index of the second half of the I/O staging
   for (int pass = 0; pass < PASSES; ++pass) {
+    if constexpr (DIRECT) {
+      // straight into the FFT layout: register e of lane t is element n = R2 e + t of the packed row pair
+      env.for_threads([&](int cta, int tid) {
+        ThreadRegs<Cfg>& r = env.regs(cta, tid);
+        const int g = tid / TG, t = tid % TG, item = pass * NG + g;
+        const int m = item / GPC, rp = cta * GPC + item % GPC;
+        const long long map = batch * MPC + m;
+        const bool live = map < p.maps;
+        const long long base = map * (long long)(N * N) + rp * N;
+#pragma unroll
+        for (int e = 0; e < R1; ++e) {
+          const int n = idx_in<Cfg>(t, e);
+          float a = 0.f, b = 0.f;
+          if (live) {
+            a = p.pred[base + n];
+            b = p.pred[base + HALF * N + n];
+            if constexpr (!DIFF) { a -= p.target[base + n]; b -= p.target[base + HALF * N + n]; }
+          }
+          r.v[e] = make_float2(a, b);
+        }
+      });
+    } else {
     if (pass > 0 || !PIPE) ffl_issue_loads<Cfg, DIFF>(env, p, batch, pass);
     env.for_threads([&](int cta, int tid) {
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
@@ -146,6 +182,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
         for (int e = 0; e < R1; ++e) r.v[e] = stg[io_slot<Cfg>(idx_in<Cfg>(t, e))];
       }
     });
+    }
     env.sync_warp();
     env.mark(0);
     env.for_threads([&](int cta, int tid) {
@@ -506,6 +543,33 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       inv_stage2<Cfg>(r, t, env.stg(cta) + g * STG);
     });
     env.sync_warp();
+    if constexpr (DIRECT) {
+      // straight from the FFT layout (element n = R2 e + t of the two rows), scaled already: 4-byte
+      // stores, 4 TG contiguous bytes per instruction and transform
+      env.mark(9);
+      env.for_threads([&](int cta, int tid) {
+        ThreadRegs<Cfg>& r = env.regs(cta, tid);
+        const int g = tid / TG, t = tid % TG, item = pass * NG + g;
+        const int m = item / GPC, rp = cta * GPC + item % GPC;
+        const long long map = map0 + m;
+        if (map < p.maps) {
+          const long long base = map * (long long)(N * N) + rp * N;
+#pragma unroll
+          for (int e = 0; e < R1; ++e) {
+            const int n = idx_in<Cfg>(t, e);
+            if (p.grad_pred) {
+              p.grad_pred[base + n] = r.v[e].x;
+              p.grad_pred[base + HALF * N + n] = r.v[e].y;
+            }
+            if (p.grad_target) {
+              p.grad_target[base + n] = -r.v[e].x;
+              p.grad_target[base + HALF * N + n] = -r.v[e].y;
+            }
+          }
+        }
+      });
+      if (pass + 1 < PASSES) gather(pass + 1);
+    } else {
     // back to float4 rows through the staging area, scaled, stored as +grad / -grad
     env.for_threads([&](int cta, int tid) {
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
@@ -552,6 +616,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
         }
       }
     });
+    }
     env.sync_warp();
     env.mark(10);
   }
