@@ -17,6 +17,63 @@
 #include "common.cuh"
 #include "ffl_core.cuh"   // packed fp32x2 helpers (pk_add / pk_mul / pk_fma / pk_dup)
 
+// Tuning constants.  The defaults are the measured optima quoted next to each kernel below; they can be
+// overridden on the nvcc command line for experiments (profiles/README.md) and nothing else reads them.
+#ifndef FAVAE_ADJ_FULL
+#define FAVAE_ADJ_FULL 0   // adjoint kernel: 0 = RS rows unrolled inside a rolled loop
+#endif
+#ifndef FAVAE_ADJ_MINB
+#define FAVAE_ADJ_MINB 5   // adjoint kernel: CTAs per SM
+#endif
+#ifndef FAVAE_FWD_FULL
+#define FAVAE_FWD_FULL 1   // forward kernel: all rows of a strip unrolled (the rolled form is 45 % slower there)
+#endif
+#ifndef FAVAE_FWD_MINB
+#define FAVAE_FWD_MINB 5   // forward kernel: CTAs per SM (96 registers)
+#endif
+#ifndef FAVAE_FWD_Q
+#define FAVAE_FWD_Q 6   // forward kernel: rows in flight from HBM per thread (register prefetch)
+#endif
+#ifndef FAVAE_FWD_TH
+#define FAVAE_FWD_TH 32   // forward kernel: strip height
+#endif
+#ifndef FAVAE_ADJ_Q
+#define FAVAE_ADJ_Q 3   // adjoint kernel: rows in flight per thread
+#endif
+#ifndef FAVAE_DIFF_MINB
+#define FAVAE_DIFF_MINB 4   // blur-difference kernel: CTAs per SM at k <= 9 (126 registers)
+#endif
+#ifndef FAVAE_ADJSIG_MINB
+#define FAVAE_ADJSIG_MINB 4   // adjoint + sigma kernel: CTAs per SM (126 registers)
+#endif
+#ifndef FAVAE_ADJSIG_FULL
+#define FAVAE_ADJSIG_FULL 0   // adjoint + sigma kernel: 0 = RS rows unrolled inside a rolled loop
+#endif
+#ifndef FAVAE_ADJSIG_Q
+#define FAVAE_ADJSIG_Q 3   // adjoint + sigma kernel: register prefetch depth when the cp.async rings are off
+#endif
+#ifndef FAVAE_ADJSIG_XQ
+#define FAVAE_ADJSIG_XQ 1   // adjoint + sigma kernel: x rows in flight in registers when the rings are off
+#endif
+#ifndef FAVAE_ADJSIG_XASYNC
+#define FAVAE_ADJSIG_XASYNC 4   // adjoint + sigma kernel: > 0 = x rows through a cp.async shared ring of (up to) that many rows
+#endif
+#ifndef FAVAE_ADJSIG_GASYNC
+#define FAVAE_ADJSIG_GASYNC 4   // adjoint + sigma kernel: gy AND x rows through cp.async rings of that depth (power of two; 0 = off)
+#endif
+#ifndef FAVAE_SIGMA_MINB
+#define FAVAE_SIGMA_MINB 4   // sigma-only kernel (FAVAE_BLUR_SIGMA=split): CTAs per SM
+#endif
+#ifndef FAVAE_SIGMA_FULL
+#define FAVAE_SIGMA_FULL 1   // sigma-only kernel: all rows unrolled
+#endif
+#ifndef FAVAE_ADJSIG_TH
+#define FAVAE_ADJSIG_TH 64   // adjoint + sigma kernel: strip height on maps of >= 128 rows
+#endif
+#ifndef FAVAE_ADJ_TH
+#define FAVAE_ADJ_TH 64   // adjoint kernel: strip height on maps of >= 128 rows
+#endif
+
 namespace favae {
 namespace blurf {
 
@@ -68,25 +125,7 @@ __device__ __forceinline__ void load_weights(const float* sigma_ptr, float* sk, 
 // adjoint: rolled RS-row unroll, 3 rows in flight, 96 registers (5 CTAs / SM), 64-row strips on large
 // maps: 0.47 ms at 4096 maps of 256^2.  (6 rows in flight at 128 registers / 4 CTAs: 0.57 ms; all rows
 // unrolled 0.71 ms; 6 rows capped at 96 registers spills: 0.67 ms.)
-#ifndef FAVAE_ADJ_FULL
-#define FAVAE_ADJ_FULL 0
-#endif
-#ifndef FAVAE_ADJ_MINB
-#define FAVAE_ADJ_MINB 5
-#endif
 template <int KS, int TH, int MODE>
-#ifndef FAVAE_FWD_FULL
-#define FAVAE_FWD_FULL 1
-#endif
-#ifndef FAVAE_FWD_MINB
-#define FAVAE_FWD_MINB 5
-#endif
-#ifndef FAVAE_FWD_Q
-#define FAVAE_FWD_Q 6
-#endif
-#ifndef FAVAE_FWD_TH
-#define FAVAE_FWD_TH 32
-#endif
 __global__ void __launch_bounds__(THREADS, MODE == MODE_ADJ ? FAVAE_ADJ_MINB : FAVAE_FWD_MINB)
 blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ /*aux*/, int h, int w, long long items,
                  int strips, const float* __restrict__ sigma, float* __restrict__ dst,
@@ -120,9 +159,6 @@ blur_fast_kernel(const float* __restrict__ src, const float* __restrict__ /*aux*
   // rows inside a rolled loop).  Every ring index is a constant.  (A cp.async shared-memory ring as
   // in blur_adjsig_kernel was measured here too: no gain for either mode - 0.474 / 0.393 ms against
   // 0.469 / 0.394 ms - these two kernels are not waiting for their loads.)
-#ifndef FAVAE_ADJ_Q
-#define FAVAE_ADJ_Q 3
-#endif
   constexpr int Q = ADJ ? FAVAE_ADJ_Q : FAVAE_FWD_Q, RS = KS + Q, NR = TH + KS - 1;
   const long long mapoff = map * (long long)h * w;
   auto load_row = [&](int r) -> float4 {
@@ -244,9 +280,6 @@ template <int P> __device__ __forceinline__ void halo_puts(float4* pa, float4* p
 // input loads (ncu: 13.5 B/element of DRAM traffic, 166 M warp instructions per 1024 maps, issue active
 // 60 %, `no_instruction` 1.5 cycles per issue: two scalar passes of a fully unrolled 40-row body are
 // instruction bound).
-#ifndef FAVAE_DIFF_MINB
-#define FAVAE_DIFF_MINB 4
-#endif
 template <int KS, int TH>
 __global__ void __launch_bounds__(THREADS, KS <= 9 ? FAVAE_DIFF_MINB : KS == 11 ? 3 : 2)   // the window is 8 KS registers
 blur_diff_kernel(const float* __restrict__ enc, const float* __restrict__ dec, int h, int w, long long items,
@@ -374,12 +407,6 @@ blur_diff_kernel(const float* __restrict__ enc, const float* __restrict__ dec, i
 // stall that remained was the x row (requested one iteration ahead into registers) arriving late;
 // two x rows in registers spill at the 128-register cap (0.90 ms), L2 prefetch hints change
 // nothing, so x now travels through a cp.async shared-memory ring 3 iterations ahead: 0.74 ms.)
-#ifndef FAVAE_ADJSIG_MINB
-#define FAVAE_ADJSIG_MINB 4
-#endif
-#ifndef FAVAE_ADJSIG_FULL
-#define FAVAE_ADJSIG_FULL 0
-#endif
 template <int KS, int TH>
 __global__ void __launch_bounds__(THREADS, FAVAE_ADJSIG_MINB)
 blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux, int h, int w, long long items,
@@ -411,22 +438,10 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
   const float* base = src + map * (long long)h * w;
   float acc_sigma = 0.f;
 
-#ifndef FAVAE_ADJSIG_Q
-#define FAVAE_ADJSIG_Q 3
-#endif
-#ifndef FAVAE_ADJSIG_XQ
-#define FAVAE_ADJSIG_XQ 1
-#endif
-#ifndef FAVAE_ADJSIG_XASYNC
-#define FAVAE_ADJSIG_XASYNC 4      // > 0: x rows through a cp.async shared ring of (up to) that many rows
-#endif
 // gy AND x rows through cp.async shared-memory rings of that depth (a power of two; 0: register
 // prefetch).  Measured at 4096 maps of 256^2: register prefetch 0.79 ms, x ring only 0.74 ms, both
 // rings depth 4 0.66 ms, depth 8 0.68 ms (and 33 KB of static shared memory, over the 48 KB launch
 // limit together with the line buffers of the narrow maps).
-#ifndef FAVAE_ADJSIG_GASYNC
-#define FAVAE_ADJSIG_GASYNC 4
-#endif
   constexpr int XQ = FAVAE_ADJSIG_XQ;
   constexpr int GD = FAVAE_ADJSIG_GASYNC;
   constexpr int Q = GD ? 0 : FAVAE_ADJSIG_Q + ((XQ - (KS + FAVAE_ADJSIG_Q) % XQ) % XQ), RS = KS + Q, NR = TH + KS - 1;
@@ -614,12 +629,6 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
 // Measured on B200 (4096 maps of 256^2, k = 9, together with the plain adjoint): rolled 15-row unroll
 // at 154 registers 1.03 ms; capped at 128 registers (4 CTAs / SM) 0.85 ms; all rows unrolled 0.95 ms;
 // both 0.69 ms.
-#ifndef FAVAE_SIGMA_MINB
-#define FAVAE_SIGMA_MINB 4
-#endif
-#ifndef FAVAE_SIGMA_FULL
-#define FAVAE_SIGMA_FULL 1
-#endif
 template <int KS, int TH>
 __global__ void __launch_bounds__(THREADS, FAVAE_SIGMA_MINB)
 blur_sigma_kernel(const float* __restrict__ src, const float* __restrict__ aux, int h, int w, long long items,
@@ -751,12 +760,6 @@ inline bool supported(int h, int w, int ks) {
 // adjoint + sigma kernel (rolled loop, so the height is free) takes taller strips on large maps: a
 // strip re-reads KS - 1 halo rows, 25 % of its loads at 32 rows, 12.5 % at 64 (1.10 -> 0.79 ms together
 // with the occupancy change above).
-#ifndef FAVAE_ADJSIG_TH
-#define FAVAE_ADJSIG_TH 64
-#endif
-#ifndef FAVAE_ADJ_TH
-#define FAVAE_ADJ_TH 64
-#endif
 inline int strip_rows(int h, int mode = MODE_FWD) {
   if (mode == MODE_ADJ_SIG && h >= 2 * FAVAE_ADJSIG_TH) return FAVAE_ADJSIG_TH;
   if (mode == MODE_ADJ && h >= 2 * FAVAE_ADJ_TH) return FAVAE_ADJ_TH;
