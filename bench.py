@@ -516,8 +516,8 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    traced = ['favae_ffl_forward', 'favae_blur_diff_forward', 'favae_blur_backward', 'favae_blur_forward',
-              'favae_vq_search_tc']
+    traced = ['favae_ffl_forward', 'favae_blur_diff_forward', 'favae_blur_backward', 'favae_blur_backward_pair',
+              'favae_blur_forward', 'favae_vq_search_tc']
     if rank == 0 and graph is None:
         _lib.start_trace(traced)
     launches0 = _lib.launch_count()
@@ -719,6 +719,10 @@ def kernel_groups(trace, wl, args, pk, steps):
     if g and wl['ksize'] == 9:
         g['traffic'] = NCU_TRAFFIC['blur_backward'][0] * e_l0
         g['traffic_source'] = NCU_TRAFFIC['blur_backward'][1]
+    # favae_blur_backward_pair(gy, x_enc, x_dec, maps, h, w, ks, ...)
+    bp = [ms for ms, a in trace.get('favae_blur_backward_pair', []) if a[3] == maps_l0 and a[4] == h0]
+    add('blur_adjoint_sigma_pair_level0', f'blur_adjsig_pair_kernel<{wl["ksize"]},64>: both sides of the level in one pass '
+        'over G: read G, enc, dec, write both gradients (20 B/element)', bp, 20.0 * e_l0)
     bf = [ms for ms, a in trace.get('favae_blur_forward', []) if a[1] == maps_l0 and a[2] == h0]
     add('blur_forward_level0', 'blur_fast_kernel forward (8 B/element)', bf, 8.0 * e_l0)
     vq = [ms for ms, a in trace.get('favae_vq_search_tc', [])]

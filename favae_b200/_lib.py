@@ -46,6 +46,7 @@ SIGNATURES = {
     'favae_blur_forward': (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
     'favae_blur_partials': (_i64, [_i64, _i32, _i32]),
     'favae_blur_backward': (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _f32, _vp, _vp, _vp, _vp, _vp]),
+    'favae_blur_backward_pair': (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'favae_blur_fast_supported': (_i32, [_i32, _i32, _i32]),
     'favae_blur_diff_forward': (_i32, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
 }

@@ -261,6 +261,31 @@ int favae_blur_diff_forward(const float* enc, const float* dec, int64_t maps, in
   return blurf::launch_diff(enc, dec, maps, h, w, ksize, sigma_enc, sigma_dec, d, (cudaStream_t)stream);
 }
 
+int favae_blur_backward_pair(const float* gy, const float* x_enc, const float* x_dec, int64_t maps, int h, int w,
+                             int ksize, const float* sigma_enc, const float* sigma_dec, const float* scale_dev,
+                             float* g_enc, float* g_dec, float* gsigma_enc, float* gsigma_dec, float* partials,
+                             void* stream) {
+  FAVAE_REQUIRE(gy && x_enc && x_dec && sigma_enc && sigma_dec && g_enc && g_dec && gsigma_enc && gsigma_dec && partials,
+                "blur_backward_pair: null pointer");
+  int rc = blur_check(maps, h, w, ksize);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (maps == 0) {
+    FAVAE_CUDA_OK(cudaMemsetAsync(gsigma_enc, 0, sizeof(float), s));
+    FAVAE_CUDA_OK(cudaMemsetAsync(gsigma_dec, 0, sizeof(float), s));
+    return 0;
+  }
+  FAVAE_REQUIRE(blurf::supported(h, w, ksize) && aligned16(gy) && aligned16(x_enc) && aligned16(x_dec) &&
+                    aligned16(g_enc) && aligned16(g_dec),
+                "blur_backward_pair: needs favae_blur_fast_supported and 16-byte aligned maps");
+  rc = blurf::launch_pair(gy, x_enc, x_dec, maps, h, w, ksize, sigma_enc, sigma_dec, g_enc, g_dec, partials, scale_dev, s);
+  if (rc) return rc;
+  const long long blocks = blurf::num_blocks(maps, h, w, blurf::MODE_ADJ_SIG);
+  rc = favae_sum_scaled(partials, blocks, 1.0, gsigma_enc, stream);
+  if (rc) return rc;
+  return favae_sum_scaled(partials + blocks, blocks, 1.0, gsigma_dec, stream);
+}
+
 int favae_blur_backward(const float* gy, const float* x, int64_t maps, int h, int w, int ksize,
                         const float* sigma, float out_scale, const float* out_scale_dev, float* gx, float* gsigma,
                         float* partials, void* stream) {

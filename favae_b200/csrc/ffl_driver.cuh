@@ -305,10 +305,18 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
         r.sum = fmaf(2.0f, sum, r.sum);
         r.mx = mx;
       }
+      // The column spectra of the LAST pass stay in the payload registers across the statistics
+      // exchange when a gradient follows: P5 starts with that pass and weights them where they are, which
+      // saves one write and one read of S for those columns (all of them for the single-pass
+      // configurations; half at N >= 256) -- the kernel is shared-memory-bandwidth bound.  Group 0 (the
+      // packed real columns 0 and N/2) always goes through S: P3 / P4 work on it there.
+      // (Loss-only calls end after P3, which reads group 0 alone: nothing else is written at all.)
+      if (!(v != 0 && (!want_grad || pass == PASSES - 1))) {
 #pragma unroll
-      for (int e = 0; e < R1; ++e) {
-        const int u = idx_out<Cfg>(t, e);
-        S[(u < HALF) ? off0 + IS * u : off1 + IS * (u - HALF)] = r.v[e];
+        for (int e = 0; e < R1; ++e) {
+          const int u = idx_out<Cfg>(t, e);
+          S[(u < HALF) ? off0 + IS * u : off1 + IS * (u - HALF)] = r.v[e];
+        }
       }
     });
     env.sync_warp();
@@ -445,7 +453,8 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
   env.mark(5);
   if (FAVAE_FFL_PF_POINT == 5) prefetch_next();
   // ---------------- P5: weight + inverse column FFTs, re-pack into Z' ----------------
-  for (int pass = 0; pass < PASSES; ++pass) {
+  for (int pi = 0; pi < PASSES; ++pi) {
+    const int pass = (pi == 0) ? PASSES - 1 : pi - 1;   // the pass P2 left in the registers comes first
     env.for_threads([&](int cta, int tid) {
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
       const int g = tid / TG, t = tid % TG, item = pass * NG + g;
@@ -456,10 +465,12 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       s_locate<Cfg>(v == 0 ? 0 : v, m, o0, off0);
       s_locate<Cfg>(v == 0 ? HALF : N - v, m, o1, off1);
       const float2* S = env.S(cta, cta);
+      if (!(pi == 0 && v != 0)) {
 #pragma unroll
-      for (int e = 0; e < R1; ++e) {
-        const int u = idx_out<Cfg>(t, e);
-        r.v[e] = S[(u < HALF) ? off0 + IS * u : off1 + IS * (u - HALF)];
+        for (int e = 0; e < R1; ++e) {
+          const int u = idx_out<Cfg>(t, e);
+          r.v[e] = S[(u < HALF) ? off0 + IS * u : off1 + IS * (u - HALF)];
+        }
       }
       if (v != 0) {                                      // group 0 was weighted in place by P4
         // the gradient scale rides on the weights (FAST: grad_scale >= 0, so it commutes with the clamp)

@@ -11,13 +11,15 @@ to pred, so:
 
   forward   d  = B_dec(dec) - B_enc(enc)              favae_blur_diff_forward   12 B/element
             G  = dL/dd, loss                          favae_ffl_forward(d, NULL) 8 B/element (in place)
-  backward  g_dec, g_sigma_dec = +adjoint/sigma(G)    favae_blur_backward(+1)   12 B/element
-            g_enc, g_sigma_enc = -adjoint/sigma(G)    favae_blur_backward(-1)   12 B/element
+  backward  g_dec, g_sigma_dec = +adjoint/sigma(G)    favae_blur_backward_pair  20 B/element
+            g_enc, g_sigma_enc = -adjoint/sigma(G)    (both sides in one pass over G)
 
-44 bytes per feature element instead of 56 for blur, blur, loss (16), adjoint+sigma, adjoint+sigma
-on materialised maps, one map-sized scratch buffer instead of four, and 4 launches instead of 5.
+40 bytes per feature element instead of 56 for blur, blur, loss (16), adjoint+sigma, adjoint+sigma
+on materialised maps, one map-sized scratch buffer instead of four, and 3 launches instead of 5.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 
@@ -100,8 +102,29 @@ class _DSLFunction(torch.autograd.Function):
             # the upstream factor (exactly 1 when the announced scale was applied) rides on the adjoint
             # kernels' output scale: G itself is never re-scaled in HBM.
             # ffl(pred = blur(dec), target = blur(enc)): +G flows to the decoder side, -G to the encoder side
-            g_dec, gs_dec = blur_backward(g, dec, sigma_dec, ksize, ctx.need[2], ctx.need[3], 1.0, s)
-            g_enc, gs_enc = blur_backward(g, enc, sigma_enc, ksize, ctx.need[0], ctx.need[1], -1.0, s)
+            if any(ctx.need[:2]) and any(ctx.need[2:]) and os.environ.get('FAVAE_DSL_PAIR', '1') not in ('', '0'):
+                # both sides in one pass over G (the normal case: features and sigmas of both sides train)
+                h, w = enc.shape[-2:]
+                maps = enc.numel() // (h * w)
+                g_enc, g_dec = torch.empty_like(enc), torch.empty_like(dec)
+                gs = torch.empty((2,), device=enc.device, dtype=torch.float32)
+                nparts = max(int(_lib.load().favae_blur_partials(maps, h, w)), 1)
+                partials = torch.empty((2 * nparts,), device=enc.device, dtype=torch.float32)
+                _lib.call('favae_blur_backward_pair', _lib.ptr(g), _lib.ptr(enc), _lib.ptr(dec), maps, h, w, ksize,
+                          _lib.ptr(sigma_enc), _lib.ptr(sigma_dec), _lib.ptr(s), _lib.ptr(g_enc), _lib.ptr(g_dec),
+                          gs.data_ptr(), gs.data_ptr() + 4, _lib.ptr(partials), _lib.stream())
+                gs_enc, gs_dec = gs[0:1], gs[1:2]
+                if not ctx.need[0]:
+                    g_enc = None
+                if not ctx.need[1]:
+                    gs_enc = None
+                if not ctx.need[2]:
+                    g_dec = None
+                if not ctx.need[3]:
+                    gs_dec = None
+            else:
+                g_dec, gs_dec = blur_backward(g, dec, sigma_dec, ksize, ctx.need[2], ctx.need[3], 1.0, s)
+                g_enc, gs_enc = blur_backward(g, enc, sigma_enc, ksize, ctx.need[0], ctx.need[1], -1.0, s)
             ctx.g = g                            # G is untouched: a second backward can reuse it
         gs_enc = gs_enc.reshape(sigma_enc.shape) if gs_enc is not None else None
         gs_dec = gs_dec.reshape(sigma_dec.shape) if gs_dec is not None else None

@@ -43,7 +43,7 @@ def main():
 
     shape = (B, 128, 256, 256)
     E = B * 128 * 256 * 256
-    if want('ffl') or want('blur_fwd') or want('blur_bwd') or want('blur_diff'):
+    if want('ffl') or want('blur_fwd') or want('blur_bwd') or want('blur_diff') or want('blur_pair'):
         p = torch.randn(shape, device=dev); t = torch.randn(shape, device=dev)
         gp = torch.empty_like(p); gt = torch.empty_like(p)
         sig = torch.tensor(3.0, device=dev)
@@ -78,6 +78,16 @@ def main():
         ms = timed(lambda: _lib.call('favae_blur_diff_forward', p.data_ptr(), t.data_ptr(), B * 128, 256, 256, 9,
                                      sig.data_ptr(), sig2.data_ptr(), gp.data_ptr(), st()), it)
         print(f'blur diff k9       {ms:8.3f} ms  {12 * E / ms / 1e6:8.1f} GB/s (12 B/elem)')
+    if want('blur_pair'):
+        gs2 = torch.empty(2, device=dev); sig2 = torch.tensor(2.5, device=dev)
+        n_p = int(_lib.load().favae_blur_partials(B * 128, 256, 256))
+        parts2 = torch.empty(2 * n_p, device=dev)
+        g = torch.randn(shape, device=dev)
+        ms = timed(lambda: _lib.call('favae_blur_backward_pair', g.data_ptr(), p.data_ptr(), t.data_ptr(), B * 128, 256, 256,
+                                     9, sig.data_ptr(), sig2.data_ptr(), None, gp.data_ptr(), gt.data_ptr(),
+                                     gs2.data_ptr(), gs2.data_ptr() + 4, parts2.data_ptr(), st()), it)
+        print(f'blur bwd pair k9   {ms:8.3f} ms  {20 * E / ms / 1e6:8.1f} GB/s (20 B/elem)')
+        del g
     if want('blur_bwd'):
         gs = torch.empty(1, device=dev)
         parts = torch.empty(int(_lib.load().favae_blur_partials(B * 128, 256, 256)), device=dev)
