@@ -214,11 +214,16 @@ class _CodebookBase(nn.Module):
         self._flush()
         self.__dict__['_prep'] = None
 
+    def _defers_ema(self, t):
+        """True when the statistics all-reduce of this call runs on the side stream and the EMA waits for
+        the next touch of the codebook."""
+        import torch.distributed as dist
+        return bool(self.use_ddp and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+                    and t.is_cuda and self.threshold_ema_dead_code == 0)
+
     def _after_stats(self, en, eh, stats):
         """Statistics of this call are ready on the current stream: all-reduce + EMA."""
-        import torch.distributed as dist
-        if self.use_ddp and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 \
-                and stats.is_cuda and self.threshold_ema_dead_code == 0:
+        if self._defers_ema(stats):
             # one all-reduce of [bins | embed_sum] (reference: two blocking ones, :419/:427 and :291/:295),
             # on a side stream; the EMA waits for it at the next touch of the codebook (_flush)
             side = _side_stream(stats.device)
@@ -389,6 +394,15 @@ class _CodebookBase(nn.Module):
             raise RuntimeError(f'favae_b200: latents on {dev} but the codebook is on {embed.device}')
         idx, en, eh = self._search_rows(xn, xh, None, n)
 
+        # When the EMA is deferred (data-parallel run: _after_stats only launches the all-reduce on the side
+        # stream), the statistics come first so that the collective also overlaps the gather of this call;
+        # otherwise the EMA would overwrite the codebook the gather still has to read (reference :415
+        # gathers before :421-438 update), so the order stays gather -> statistics -> EMA.
+        early = self.training and self._defers_ema(x)
+        if early:
+            stats = self._code_stats(xn, idx, n, self._buf('stats', (k * (d + 1),), torch.float32, dev))
+            self._after_stats(en, eh, stats)
+
         out = torch.empty_like(x)
         # written in full by favae_vq_gather_st when the loss is wanted
         loss_sum = (torch.empty if want_loss else torch.zeros)((1,), device=dev, dtype=torch.float32)
@@ -398,7 +412,7 @@ class _CodebookBase(nn.Module):
                   int(straight_through), _lib.ptr(out), _lib.ptr(partials),
                   _lib.ptr(loss_sum) if want_loss else None, _lib.stream())
 
-        if self.training:
+        if self.training and not early:
             stats = self._code_stats(xn, idx, n, self._buf('stats', (k * (d + 1),), torch.float32, dev))
             self._after_stats(en, eh, stats)
             self._expire_codes(xn)
