@@ -70,6 +70,15 @@
 #ifndef FAVAE_ADJSIG_TH
 #define FAVAE_ADJSIG_TH 64   // adjoint + sigma kernel: strip height on maps of >= 128 rows
 #endif
+#ifndef FAVAE_DIFF_U
+#define FAVAE_DIFF_U 4   // blur-difference kernel: rows per rolled iteration (0 = KS, the renamed ring)
+#endif
+#ifndef FAVAE_PAIR_U
+#define FAVAE_PAIR_U 2   // paired adjoint + sigma kernel: rows per rolled iteration (0 = KS, the renamed ring)
+#endif
+#ifndef FAVAE_PAIR_TH
+#define FAVAE_PAIR_TH 128   // paired adjoint + sigma kernel: strip height on maps of >= 256 rows
+#endif
 #ifndef FAVAE_ADJ_TH
 #define FAVAE_ADJ_TH 64   // adjoint kernel: strip height on maps of >= 128 rows
 #endif
@@ -78,7 +87,7 @@ namespace favae {
 namespace blurf {
 
 constexpr int THREADS = 128;
-constexpr int MODE_FWD = 0, MODE_ADJ = 1, MODE_ADJ_SIG = 2, MODE_SIGMA = 3;
+constexpr int MODE_FWD = 0, MODE_ADJ = 1, MODE_ADJ_SIG = 2, MODE_SIGMA = 3, MODE_PAIR = 4;
 constexpr int LPAD = 8;                          // left halo slots of a shared line (>= p, 16B aligned)
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {
@@ -309,7 +318,10 @@ blur_diff_kernel(const float* __restrict__ enc, const float* __restrict__ dec, i
   const long long mapoff = map * (long long)h * w;
   const float* ebase = enc + mapoff;
   const float* dbase = dec + mapoff;
-  constexpr int GD = 4, RS = KS, NR = TH + KS - 1;
+  // rows per rolled iteration: see blur_adjsig_pair_kernel (U < KS: shifted ring, small body)
+  constexpr int U = (FAVAE_DIFF_U > 0 && FAVAE_DIFF_U < KS) ? FAVAE_DIFF_U : KS;
+  constexpr bool SHIFT = U != KS;
+  constexpr int GD = 4, RS = SHIFT ? KS - 1 + U : KS, NR = TH + KS - 1;
   __shared__ float4 ering[GD][THREADS], dring[GD][THREADS];
   auto issue_rows = [&](int r) {
     if (live && r < NR) {
@@ -330,22 +342,23 @@ blur_diff_kernel(const float* __restrict__ enc, const float* __restrict__ dec, i
 #pragma unroll
     for (int c = 0; c < 4; ++c) ring[q][c] = make_float2(0.f, 0.f);
 #pragma unroll 1
-  for (int r0 = 0; r0 < NR; r0 += RS) {
+  for (int r0 = 0; r0 < NR; r0 += U) {
 #pragma unroll
-    for (int u = 0; u < RS; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int r = r0 + u;
-      if (r >= NR) break;
+      if (NR % U != 0 && r >= NR) break;
       issue_rows(r + GD - 1);
       asm volatile("cp.async.wait_group %0;" ::"n"(GD - 1) : "memory");
       {
         float4 e = make_float4(0.f, 0.f, 0.f, 0.f), d = e;
         if (live) { e = ering[r & (GD - 1)][threadIdx.x]; d = dring[r & (GD - 1)][threadIdx.x]; }
-        ring[u][0] = make_float2(e.x, d.x); ring[u][1] = make_float2(e.y, d.y);
-        ring[u][2] = make_float2(e.z, d.z); ring[u][3] = make_float2(e.w, d.w);
+        float2 (&nw)[4] = ring[SHIFT ? KS - 1 + u : u];
+        nw[0] = make_float2(e.x, d.x); nw[1] = make_float2(e.y, d.y);
+        nw[2] = make_float2(e.z, d.z); nw[3] = make_float2(e.w, d.w);
       }
       if (r < KS - 1) continue;
       const int yo = y0 + r - (KS - 1);            // output row of this iteration
-#define FAVAE_WIN(t) ring[(u + 1 + (t)) % RS]
+#define FAVAE_WIN(t) ring[SHIFT ? u + (t) : (u + 1 + (t)) % RS]
       // ---- vertical pass over the mirrored window, both maps per instruction
       float2 acc[4];
 #pragma unroll
@@ -386,6 +399,12 @@ blur_diff_kernel(const float* __restrict__ enc, const float* __restrict__ dec, i
       }
       if (live && yo < h)
         __stcs(reinterpret_cast<float4*>(dst + mapoff + (long long)yo * w + x0), make_float4(o[0], o[1], o[2], o[3]));
+    }
+    if constexpr (SHIFT) {
+#pragma unroll
+      for (int q = 0; q < KS - 1; ++q)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ring[q][c] = ring[q + U][c];
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -673,7 +692,12 @@ blur_adjsig_pair_kernel(const float* __restrict__ gy, const float* __restrict__ 
   const float e0 = tx == 0 ? 2.f : 1.f, e3 = tx == tpi - 1 ? 2.f : 1.f;     // E, columns
   const float d0 = tx == 0 ? 0.5f : 1.f, d3 = tx == tpi - 1 ? 0.5f : 1.f;   // D, columns
 
-  constexpr int GD = 4, RS = KS, NR = TH + KS - 1;
+  // Rows per rolled iteration.  U == KS: the window ring is renamed (every ring index a constant), at the
+  // price of a KS-row body.  U < KS: the ring holds KS - 1 + U rows and is shifted down by U rows with
+  // register moves after every iteration (4 (KS - 1) / U moves per row), which keeps the body small.
+  constexpr int U = (FAVAE_PAIR_U > 0 && FAVAE_PAIR_U < KS) ? FAVAE_PAIR_U : KS;
+  constexpr bool SHIFT = U != KS;
+  constexpr int GD = 4, RS = SHIFT ? KS - 1 + U : KS, NR = TH + KS - 1;
   __shared__ float4 gring[GD][THREADS], xring[2][GD][THREADS];
   auto issue_rows = [&](int r) {
     if (live && r < NR) {
@@ -697,21 +721,22 @@ blur_adjsig_pair_kernel(const float* __restrict__ gy, const float* __restrict__ 
 #pragma unroll
   for (int q = 0; q < RS; ++q) ring[q] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-  for (int r0 = 0; r0 < NR; r0 += RS) {
+  for (int r0 = 0; r0 < NR; r0 += U) {
 #pragma unroll
-    for (int u = 0; u < RS; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int r = r0 + u;
-      if (r >= NR) break;
+      if (NR % U != 0 && r >= NR) break;
+      const int slot_new = SHIFT ? KS - 1 + u : u;
       issue_rows(r + GD - 1);
       asm volatile("cp.async.wait_group %0;" ::"n"(GD - 1) : "memory");
-      ring[u] = live ? gring[r & (GD - 1)][threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+      ring[slot_new] = live ? gring[r & (GD - 1)][threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
       {                                            // E, rows: doubled when the row enters the window
         const int ry = reflect_idx(y0 - P + r, h);
-        if (ry == 0 || ry == h - 1) { float4& b = ring[u]; b.x *= 2.f; b.y *= 2.f; b.z *= 2.f; b.w *= 2.f; }
+        if (ry == 0 || ry == h - 1) { float4& b = ring[slot_new]; b.x *= 2.f; b.y *= 2.f; b.z *= 2.f; b.w *= 2.f; }
       }
       if (r < KS - 1) continue;
       const int yo = y0 + r - (KS - 1);            // output row of this iteration
-#define FAVAE_WIN(t) ring[(u + 1 + (t)) % RS]
+#define FAVAE_WIN(t) ring[SHIFT ? u + (t) : (u + 1 + (t)) % RS]
       // ---- vertical pass: the mirrored pre-adds are shared by the two sides
       float2 s01[P > 0 ? P : 1], s23[P > 0 ? P : 1];
 #pragma unroll
@@ -783,6 +808,10 @@ blur_adjsig_pair_kernel(const float* __restrict__ gy, const float* __restrict__ 
           acc_sigma[sd] = fmaf(xrow.x, z[0], fmaf(xrow.y, z[1], fmaf(xrow.z, z[2], fmaf(xrow.w, z[3], acc_sigma[sd]))));
         }
       }
+    }
+    if constexpr (SHIFT) {
+#pragma unroll
+      for (int q = 0; q < KS - 1; ++q) ring[q] = ring[q + U];
     }
   }
 #pragma unroll
@@ -939,6 +968,10 @@ inline bool supported(int h, int w, int ks) {
 // strip re-reads KS - 1 halo rows, 25 % of its loads at 32 rows, 12.5 % at 64 (1.10 -> 0.79 ms together
 // with the occupancy change above).
 inline int strip_rows(int h, int mode = MODE_FWD) {
+  if (mode == MODE_PAIR) {
+    if (FAVAE_PAIR_TH > FAVAE_ADJSIG_TH && h >= 2 * FAVAE_PAIR_TH) return FAVAE_PAIR_TH;
+    mode = MODE_ADJ_SIG;
+  }
   if (mode == MODE_ADJ_SIG && h >= 2 * FAVAE_ADJSIG_TH) return FAVAE_ADJSIG_TH;
   if (mode == MODE_ADJ && h >= 2 * FAVAE_ADJ_TH) return FAVAE_ADJ_TH;
   if (mode == MODE_FWD && FAVAE_FWD_TH > 32 && h >= 2 * FAVAE_FWD_TH) return FAVAE_FWD_TH;
@@ -1018,9 +1051,11 @@ static int launch_pair(const float* gy, const float* xe, const float* xd, long l
                        const float* scale_dev, cudaStream_t s) {
 #define FAVAE_BLUR_CASE(KS)                                                                                        \
   case KS:                                                                                                         \
-    return strip_rows(h, MODE_ADJ_SIG) == FAVAE_ADJSIG_TH                                                          \
+    if (FAVAE_PAIR_TH > FAVAE_ADJSIG_TH && strip_rows(h, MODE_PAIR) == FAVAE_PAIR_TH)                              \
+      return launch_pair_one<KS, FAVAE_PAIR_TH>(gy, xe, xd, maps, h, w, se, sd, ge, gd, partials, scale_dev, s);   \
+    return strip_rows(h, MODE_PAIR) == FAVAE_ADJSIG_TH                                                             \
                ? launch_pair_one<KS, FAVAE_ADJSIG_TH>(gy, xe, xd, maps, h, w, se, sd, ge, gd, partials, scale_dev, s) \
-           : strip_rows(h, MODE_ADJ_SIG) == 16                                                                     \
+           : strip_rows(h, MODE_PAIR) == 16                                                                        \
                ? launch_pair_one<KS, 16>(gy, xe, xd, maps, h, w, se, sd, ge, gd, partials, scale_dev, s)            \
                : launch_pair_one<KS, 32>(gy, xe, xd, maps, h, w, se, sd, ge, gd, partials, scale_dev, s);
   switch (ks) {

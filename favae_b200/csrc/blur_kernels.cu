@@ -280,7 +280,7 @@ int favae_blur_backward_pair(const float* gy, const float* x_enc, const float* x
                 "blur_backward_pair: needs favae_blur_fast_supported and 16-byte aligned maps");
   rc = blurf::launch_pair(gy, x_enc, x_dec, maps, h, w, ksize, sigma_enc, sigma_dec, g_enc, g_dec, partials, scale_dev, s);
   if (rc) return rc;
-  const long long blocks = blurf::num_blocks(maps, h, w, blurf::MODE_ADJ_SIG);
+  const long long blocks = blurf::num_blocks(maps, h, w, blurf::MODE_PAIR);
   rc = favae_sum_scaled(partials, blocks, 1.0, gsigma_enc, stream);
   if (rc) return rc;
   return favae_sum_scaled(partials + blocks, blocks, 1.0, gsigma_dec, stream);

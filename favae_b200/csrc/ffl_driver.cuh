@@ -17,6 +17,8 @@
 //   env.s_put(cta, entry, at, v) / env.s_get(cta, entry, at)   S[column of entry][at] across the cluster
 //   env.twiddle(j, n)    e^{-2 pi i j / n}
 //   env.prefetch_l2(ptr, bytes)   hint: bring a 16-byte-aligned global range into L2
+//   env.fence_async() / env.bulk_store(gdst, ssrc, bytes) / env.bulk_commit() / env.bulk_wait_read():
+//                        bulk async copy of a staged row to global memory (the host copies at once)
 #pragma once
 
 #include "ffl_core.cuh"
@@ -91,19 +93,41 @@ FAVAE_HD void ffl_issue_loads(Env& env, const FflParams& p, long long batch, int
 // two-input form 1.29 -> 1.35 ms (twice the loads and stores), loss only 0.72 -> 0.74 ms; 128^2
 // two-input 0.74 -> 0.78 ms; 512^2 two-input 2.15 -> 2.05 ms.  Hence: the single-input form from
 // 256^2 up, and 512^2 always.
+#ifndef FAVAE_FFL_DIRECT_LOAD
+#define FAVAE_FFL_DIRECT_LOAD 1
+#endif
+#ifndef FAVAE_FFL_DIRECT_STORE
+#define FAVAE_FFL_DIRECT_STORE 1
+#endif
 template <class Cfg, bool DIFF> struct FflDirect {
   static constexpr bool value = Cfg::DIRECT_IO_OK && ((DIFF && Cfg::N >= 256) || Cfg::N >= 512);
+  static constexpr bool load = value && FAVAE_FFL_DIRECT_LOAD, store = value && FAVAE_FFL_DIRECT_STORE;
+};
+// Bulk stores: the gradient rows of a pass are laid out as whole rows in the group's (idle) FFT staging
+// area with 4-byte shared-memory stores and leave through ONE bulk async copy per row (cp.async.bulk,
+// 4 N bytes) issued by the group's first lane, instead of 2 R1 four-byte global stores per thread whose
+// issue alone took 12.6 % of the map time (the LSU queue backs up: lg_throttle; phase stamps of
+// profiles/tools/ffl_phase_timing.cu).  Odd groups shift their rows by 16 floats so that the two groups of
+// a warp write disjoint banks.  The staging area is handed back when the copy has READ it
+// (wait_group.read), which is awaited just before the next exchange writes there.
+#ifndef FAVAE_FFL_BULK_STORE
+#define FAVAE_FFL_BULK_STORE 1
+#endif
+template <class Cfg, bool DIFF> struct FflBulk {
+  static constexpr bool value = FAVAE_FFL_BULK_STORE && DIFF && FflDirect<Cfg, DIFF>::load && FflDirect<Cfg, DIFF>::store &&
+                                (2 * Cfg::N + 16 <= 2 * Cfg::R1 * Cfg::STG_STRIDE);
 };
 template <class Cfg, bool DIFF> struct FflPipe {
   // the single-input form has the registers to keep the next map's first pass in flight under the last
   // gradient stores of the current one (the two-input form spills at 512 threads, see Cfg::PIPELINE_LOADS)
   static constexpr bool value =
-      !FflDirect<Cfg, DIFF>::value && (Cfg::PIPELINE_LOADS || (DIFF && Cfg::C == 2 && FAVAE_FFL_DIFF_PIPE));
+      !FflDirect<Cfg, DIFF>::load && (Cfg::PIPELINE_LOADS || (DIFF && Cfg::C == 2 && FAVAE_FFL_DIFF_PIPE));
 };
 template <class Cfg, bool FAST = false, bool DIFF = false, class Env>
 FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long long next_batch = -1) {
   constexpr bool PIPE = FflPipe<Cfg, DIFF>::value;
-  constexpr bool DIRECT = FflDirect<Cfg, DIFF>::value;
+  constexpr bool DIRECT = FflDirect<Cfg, DIFF>::load, DIRECT_ST = FflDirect<Cfg, DIFF>::store;
+  constexpr bool BULK = FflBulk<Cfg, DIFF>::value;
   constexpr int N = Cfg::N, R1 = Cfg::R1, TG = Cfg::TG, NG = Cfg::NG, HALF = Cfg::HALF;
   constexpr int C = Cfg::C, MPC = Cfg::MPC, T = Cfg::THREADS, PASSES = Cfg::PASSES;
   constexpr int GPC = HALF / C;                 // row pairs / column groups per CTA and map
@@ -182,6 +206,10 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
         for (int e = 0; e < R1; ++e) r.v[e] = stg[io_slot<Cfg>(idx_in<Cfg>(t, e))];
       }
     });
+    }
+    if constexpr (BULK) {
+      // the previous map's last gradient rows must have left the staging area
+      if (pass == 0) env.for_threads([&](int, int tid) { if (tid % TG == 0) env.bulk_wait_read(); });
     }
     env.sync_warp();
     env.mark(0);
@@ -554,7 +582,38 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       inv_stage2<Cfg>(r, t, env.stg(cta) + g * STG);
     });
     env.sync_warp();
-    if constexpr (DIRECT) {
+    if constexpr (BULK) {
+      env.mark(9);
+      env.for_threads([&](int cta, int tid) {
+        ThreadRegs<Cfg>& r = env.regs(cta, tid);
+        const int g = tid / TG, t = tid % TG;
+        float* row = reinterpret_cast<float*>(env.stg(cta) + g * STG) + ((g & 1) ? 16 : 0);
+#pragma unroll
+        for (int e = 0; e < R1; ++e) {
+          const int n = idx_in<Cfg>(t, e);
+          row[n] = r.v[e].x;
+          row[N + n] = r.v[e].y;
+        }
+        env.fence_async();                       // generic-proxy writes -> visible to the bulk copy
+      });
+      env.sync_warp();
+      env.for_threads([&](int cta, int tid) {
+        const int g = tid / TG, t = tid % TG, item = pass * NG + g;
+        const int m = item / GPC, rp = cta * GPC + item % GPC;
+        const long long map = map0 + m;
+        if (t == 0 && map < p.maps) {
+          const float* row = reinterpret_cast<const float*>(env.stg(cta) + g * STG) + ((g & 1) ? 16 : 0);
+          const long long base = map * (long long)(N * N) + rp * N;
+          env.bulk_store(p.grad_pred + base, row, N * sizeof(float));
+          env.bulk_store(p.grad_pred + base + HALF * N, row + N, N * sizeof(float));
+          env.bulk_commit();
+        }
+      });
+      if (pass + 1 < PASSES) {
+        gather(pass + 1);
+        env.for_threads([&](int, int tid) { if (tid % TG == 0) env.bulk_wait_read(); });
+      }
+    } else if constexpr (DIRECT_ST) {
       // straight from the FFT layout (element n = R2 e + t of the two rows), scaled already: 4-byte
       // stores, 4 TG contiguous bytes per instruction and transform
       env.mark(9);

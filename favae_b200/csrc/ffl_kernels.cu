@@ -100,6 +100,13 @@ template <class Cfg> struct DevEnv {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"((unsigned)bytes) : "memory");
 #endif
   }
+  __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+  __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, size_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"((unsigned)bytes) : "memory");
+  }
+  __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+  __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
   __device__ __forceinline__ float2 twiddle(int j, int n) {
     float s, c;
     sincospif(-2.0f * (float)j / (float)n, &s, &c);
@@ -136,6 +143,7 @@ ffl_kernel(const FflParams p) {
   if (FflPipe<Cfg, DIFF>::value && first < batches) ffl_issue_loads<Cfg, DIFF>(env, p, first, 0);
   for (long long b = first; b < batches; b += stride)
     ffl_map_batch<Cfg, FAST, DIFF>(env, p, b, b + stride < batches ? b + stride : -1);
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staged gradient rows have left shared memory
   env.cluster_wait();                            // nobody leaves while a peer may still read its S
 #ifdef FAVAE_FFL_TIMING
   __syncthreads();

@@ -9,6 +9,7 @@
 
 int main(int argc, char** argv) {
   const int B = argc > 1 ? atoi(argv[1]) : 8;
+  const bool diff = argc > 2 && atoi(argv[2]) != 0;      // single-input form: d -> G (fused DSL level)
   const long long maps = (long long)B * 128, E = maps * 256 * 256;
   float *p, *t, *gp, *gt, *ml;
   cudaMalloc(&p, E * 4); cudaMalloc(&t, E * 4); cudaMalloc(&gp, E * 4); cudaMalloc(&gt, E * 4);
@@ -25,11 +26,12 @@ int main(int argc, char** argv) {
     std::vector<long long> zero(16 * 1024, 0);
     cudaMemcpyToSymbol(favae::favae_ffl_phase_cycles, zero.data(), zero.size() * 8);
     cudaEventRecord(a);
-    int rc = favae_ffl_forward(p, t, maps, 256, 256, 1.0f, 0, 1e-3f, ml, gp, gt, nullptr, nullptr, nullptr);
+    int rc = diff ? favae_ffl_forward(p, nullptr, maps, 256, 256, 1.0f, 0, 1e-3f, ml, gp, nullptr, nullptr, nullptr, nullptr)
+                  : favae_ffl_forward(p, t, maps, 256, 256, 1.0f, 0, 1e-3f, ml, gp, gt, nullptr, nullptr, nullptr);
     cudaEventRecord(b);
     cudaEventSynchronize(b);
     float ms; cudaEventElapsedTime(&ms, a, b);
-    printf("rc=%d  %.3f ms  %.1f GB/s algorithmic\n", rc, ms, 16.0 * E / ms / 1e6);
+    printf("rc=%d  %.3f ms  %.1f GB/s algorithmic\n", rc, ms, (diff ? 8.0 : 16.0) * E / ms / 1e6);
   }
   {  // checksums, to compare build variants
     std::vector<float> hl(maps), hg(65536);

@@ -38,6 +38,10 @@ template <class Cfg> struct HostEnv {
   void s_put(int cta, unsigned int e, int at, float2 v) { S(cta, (int)(e >> 24))[(int)(e & 0xFFFFFFu) + at] = v; }
   float2 s_get(int cta, unsigned int e, int at) { return S(cta, (int)(e >> 24))[(int)(e & 0xFFFFFFu) + at]; }
   void prefetch_l2(const void*, size_t) {}
+  void fence_async() {}
+  void bulk_store(void* gdst, const void* ssrc, size_t bytes) { std::memcpy(gdst, ssrc, bytes); }
+  void bulk_commit() {}
+  void bulk_wait_read() {}
   ThreadRegs<Cfg>& regs(int cta, int tid) { return regs_[cta * Cfg::THREADS + tid]; }
   float2* S(int, int owner) { return S_.data() + (size_t)owner * Cfg::S_FLOAT2; }
   float2* stg(int cta) { return stg_.data() + (size_t)cta * (Cfg::STG_FLOAT2 + 2); }
