@@ -133,13 +133,16 @@ class HotPath:
         dec = [t.detach().requires_grad_(True) for t in inp['dec']]
         # ---- stage 0, in the order of VQGANFCM.forward(stage=0): encoder (features + blurs),
         # quantizer, decoder (features + blurs), losses (train_favae.py:75-99)
-        enc_b = [blur(enc[i], self.enc_sigmas[i], k) for i in range(4)]
+        # (sigma_element(sigmas, i) is what the patched _gaussian_blur does for the reference's `self.sigmas[i]`)
+        sig = self.fb.gaussian_blur.sigma_element
+        enc_b = [blur(enc[i], sig(self.enc_sigmas, i), k) for i in range(4)]
         _, _, loss_q = self.vq(z)
-        dec_b = [blur(dec[i], self.dec_sigmas[i], k) for i in range(4)]
-        loss = COMMIT_W * loss_q.sum()
+        dec_b = [blur(dec[i], sig(self.dec_sigmas, i), k) for i in range(4)]
+        # (1,)-shaped terms added up as train_favae.py:79-101 does
+        loss = COMMIT_W * loss_q
         loss = loss + self.vl.recon_ffl_loss(self.ffl, inp['x'], x_recon)
         loss_dsl, _ = self.vl.recon_ffl_features_loss(self.dsl, enc_b, dec_b, self.device)
-        loss = loss + loss_dsl.sum()
+        loss = loss + loss_dsl
         loss.backward()
         # ---- stage 1
         with torch.no_grad():
@@ -504,6 +507,8 @@ def main():
             graph = None
             hp.step = eager_step
             graph_note = f'eager steps: CUDA graph capture failed ({type(exc).__name__}: {str(exc)[:120]})'
+            print(graph_note, file=sys.stderr, flush=True)
+            hp.vq._codebook.__dict__['_pending'] = None   # an event recorded inside the aborted capture is void
             torch.cuda.synchronize()
         ok = torch.tensor([1.0 if graph is not None else 0.0], device=device)
         if world > 1:
@@ -671,6 +676,8 @@ NCU_TRAFFIC = {
     'ffl_diff': (7.12, 'ncu --set full, ffl_kernel<256> single-input form: 268.5 MB read + 209.1 MB written for 1024 maps '
                        'of 256^2 = 7.12 B/element, part of the last gradient stores still in L2 when the kernel ends '
                        '(profiles/ncu_r2_ffldiff_raw.csv)'),
+    'blur_pair': (19.67, 'ncu --set full, blur_adjsig_pair_kernel<9,128> (2-row body): 813.7 MB read + 506.5 MB written for '
+                         '1024 maps of 256^2 = 19.67 B/element (profiles/ncu_r2b_blur_pair_raw.csv)'),
     'ffl2': (15.48, 'ncu --set full, ffl_kernel<256> two-input form: 15.48 B/element (profiles/ncu_r1_summary.md)')}
 
 
@@ -721,8 +728,11 @@ def kernel_groups(trace, wl, args, pk, steps):
         g['traffic_source'] = NCU_TRAFFIC['blur_backward'][1]
     # favae_blur_backward_pair(gy, x_enc, x_dec, maps, h, w, ks, ...)
     bp = [ms for ms, a in trace.get('favae_blur_backward_pair', []) if a[3] == maps_l0 and a[4] == h0]
-    add('blur_adjoint_sigma_pair_level0', f'blur_adjsig_pair_kernel<{wl["ksize"]},64>: both sides of the level in one pass '
-        'over G: read G, enc, dec, write both gradients (20 B/element)', bp, 20.0 * e_l0)
+    g = add('blur_adjoint_sigma_pair_level0', f'blur_adjsig_pair_kernel<{wl["ksize"]},{128 if h0 >= 256 else 64}>: both sides '
+            'of the level in one pass over G: read G, enc, dec, write both gradients (20 B/element)', bp, 20.0 * e_l0)
+    if g and wl['ksize'] == 9 and h0 == 256:
+        g['traffic'] = NCU_TRAFFIC['blur_pair'][0] * e_l0
+        g['traffic_source'] = NCU_TRAFFIC['blur_pair'][1]
     bf = [ms for ms, a in trace.get('favae_blur_forward', []) if a[1] == maps_l0 and a[2] == h0]
     add('blur_forward_level0', 'blur_fast_kernel forward (8 B/element)', bf, 8.0 * e_l0)
     vq = [ms for ms, a in trace.get('favae_vq_search_tc', [])]

@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 
-__all__ = ['gaussian_blur_reflect', 'lazy_gaussian_blur', 'LazyBlur', 'install_reference_blur']
+__all__ = ['gaussian_blur_reflect', 'lazy_gaussian_blur', 'LazyBlur', 'install_reference_blur', 'sigma_element']
 
 
 _SIGMA_CACHE = {}
@@ -165,6 +165,33 @@ def lazy_gaussian_blur(x, sigma, kernel_size):
     return LazyBlur(x, sigma, kernel_size)
 
 
+def sigma_element(sigmas, i):
+    """``sigmas[i]`` of a sigma vector (``nn.Parameter`` of one value per FCM level, models/vqgan_fcm.py:67,76,
+    models/codec.py:215,575,898,1027) taken through ONE ``unbind`` per (vector, version): autograd then builds
+    the vector's gradient with a single ``stack`` instead of a zero-filled vector, a copy and an accumulation
+    per level (22 tiny launches per step for the two sigma vectors of the DSL model).  The views are cached
+    per vector object and dropped as soon as it is written (optimizer step) or the grad mode changes."""
+    if not torch.is_tensor(sigmas) or sigmas.dim() != 1:
+        return sigmas[i]
+    # (autograd runs a node's backward on the stream of its forward: views made on another stream -- e.g.
+    # before a CUDA graph capture -- are not reused)
+    stream = torch.cuda.current_stream(sigmas.device).cuda_stream if sigmas.is_cuda else 0
+    key = (sigmas._version, torch.is_grad_enabled() and sigmas.requires_grad, sigmas.data_ptr(), stream)
+    cached = _UNBOUND.get(id(sigmas))
+    if cached is None or cached[0] is not sigmas or cached[1] != key:
+        if len(_UNBOUND) > 64:
+            _UNBOUND.clear()
+        # the stale views go first: they keep the vector's AccumulateGrad node (and its stream) alive, and the
+        # new views must not be wired to it
+        _UNBOUND.pop(id(sigmas), None)
+        cached = None
+        cached = _UNBOUND[id(sigmas)] = (sigmas, key, sigmas.unbind(0))
+    return cached[2][i]
+
+
+_UNBOUND = {}
+
+
 def _blur_method(self, x, i, device=None):
     """Signature of the reference ``_gaussian_blur(self, x, i[, device])``.  Returns the deferred
     handle: the only consumer in the reference is the DSL loss wrapper.  ``FAVAE_LAZY_BLUR=0`` selects
@@ -172,8 +199,8 @@ def _blur_method(self, x, i, device=None):
     autograd graph of the module outputs and cannot see through a handle)."""
     import os
     if os.environ.get('FAVAE_LAZY_BLUR', '1') in ('', '0'):
-        return gaussian_blur_reflect(x, self.sigmas[i], self.kernel_size)
-    return lazy_gaussian_blur(x, self.sigmas[i], self.kernel_size)
+        return gaussian_blur_reflect(x, sigma_element(self.sigmas, i), self.kernel_size)
+    return lazy_gaussian_blur(x, sigma_element(self.sigmas, i), self.kernel_size)
 
 
 def install_reference_blur(*classes):

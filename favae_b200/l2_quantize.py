@@ -183,7 +183,8 @@ class _CodebookBase(nn.Module):
         stats, en, eh, done = pending
         with torch.cuda.device(stats.device):
             torch.cuda.current_stream(stats.device).wait_event(done)
-            self._ema_update(en, eh, stats)
+            if en is not None:                   # (en is None: the side stream already applied the update)
+                self._ema_update(en, eh, stats)
 
     def _save_to_state_dict(self, *args, **kwargs):
         self._flush()
@@ -221,6 +222,10 @@ class _CodebookBase(nn.Module):
         return bool(self.use_ddp and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
                     and t.is_cuda and self.threshold_ema_dead_code == 0)
 
+    def _ema_on_side_stream(self, t):
+        return bool(t.is_cuda and self.threshold_ema_dead_code == 0 and self.cosine
+                    and os.environ.get('FAVAE_EMA_STREAM', '1') not in ('', '0'))
+
     def _after_stats(self, en, eh, stats):
         """Statistics of this call are ready on the current stream: all-reduce + EMA."""
         if self._defers_ema(stats):
@@ -236,6 +241,18 @@ class _CodebookBase(nn.Module):
             return
         if self.use_ddp:
             _dist.all_reduce_stats(stats)      # raises like the reference without a process group
+        if self._ema_on_side_stream(stats):
+            # Single process: nothing of this call reads the updated codebook (its outputs use the
+            # pre-update one, reference :415 before :421-438), so the update runs on the side stream next to
+            # whatever the caller does after the quantizer; the next touch of the codebook waits for it.
+            side = _side_stream(stats.device)
+            side.wait_stream(torch.cuda.current_stream(stats.device))
+            with torch.cuda.stream(side):
+                self._ema_update(en, eh, stats)
+                done = torch.cuda.Event()
+                done.record(side)
+            self.__dict__['_pending'] = (stats, None, None, done)
+            return
         self._ema_update(en, eh, stats)
 
     # -- kernels --------------------------------------------------------------------------

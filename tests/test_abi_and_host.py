@@ -133,3 +133,32 @@ def test_adjoint_as_forward_stencil_identity():
         g = torch.randn(w, dtype=torch.float64, generator=g0)
         (fwd1d(x, k) * g).sum().backward()
         assert (x.grad - adjoint_by_forward_stencil(g, k)).abs().max() < 1e-12, (w, p)
+
+
+def test_sigma_element_is_select_with_one_autograd_node():
+    """favae_b200.gaussian_blur.sigma_element(sigmas, i) == sigmas[i] (value and gradient), through one
+    cached unbind per (vector, version); an in-place write (optimizer step) or a grad-mode change drops
+    the cached views."""
+    import torch
+    from favae_b200.gaussian_blur import sigma_element
+    s = torch.nn.Parameter(torch.tensor([3.0, 2.0, 1.5, 0.5]))
+    w = torch.tensor([1.0, -2.0, 0.5, 4.0])
+    els = [sigma_element(s, i) for i in range(4)]
+    assert len({e.grad_fn for e in els}) == 1                      # one UnbindBackward for the four views
+    sum(w[i] * els[i] ** 2 for i in range(4)).backward()
+    ref = torch.nn.Parameter(s.detach().clone())
+    sum(w[i] * ref[i] ** 2 for i in range(4)).backward()
+    assert torch.equal(s.grad, ref.grad)
+    # a second forward / backward through the cached views (no write in between: the benchmark's case)
+    s.grad = None
+    (sigma_element(s, 1) * 3.0).backward()
+    assert torch.equal(s.grad, torch.tensor([0.0, 3.0, 0.0, 0.0]))
+    first = sigma_element(s, 0)
+    with torch.no_grad():
+        s.add_(1.0)                                                 # optimizer step
+    again = sigma_element(s, 0)
+    assert again is not first and float(again.detach()) == 4.0
+    with torch.no_grad():
+        assert sigma_element(s, 2).grad_fn is None                  # (like s[2] under no_grad)
+    assert sigma_element(s, 2).grad_fn is not None
+    assert float(sigma_element([1.0, 2.0], 1)) == 2.0               # anything else: plain indexing
