@@ -276,9 +276,8 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
       const int g = tid / TG, t = tid % TG, item = pass * NG + g;
       const int m = item / GPC, v = cta * GPC + item % GPC;
-      int o0, o1, off0, off1;
-      s_locate<Cfg>(v == 0 ? 0 : v, m, o0, off0);
-      s_locate<Cfg>(v == 0 ? HALF : N - v, m, o1, off1);
+      int off0, off1;
+      s_group_offsets<Cfg>(item % GPC, m, off0, off1);
       const float2* S = env.S(cta, cta);
       if (v == 0) {                                      // packed real columns 0 and N/2
 #pragma unroll
@@ -308,9 +307,8 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
       const int g = tid / TG, t = tid % TG, item = pass * NG + g;
       const int m = item / GPC, v = cta * GPC + item % GPC;
-      int o0, o1, off0, off1;
-      s_locate<Cfg>(v == 0 ? 0 : v, m, o0, off0);
-      s_locate<Cfg>(v == 0 ? HALF : N - v, m, o1, off1);
+      int off0, off1;
+      s_group_offsets<Cfg>(item % GPC, m, off0, off1);
       float2* S = env.S(cta, cta);
       fwd_stage2<Cfg>(r, t, env.stg(cta) + g * STG);
       // out-layout register e holds u = idx_out(t, e); u and u + N/2 sit PO_OUT registers apart
@@ -489,9 +487,8 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       const int m = item / GPC, v = cta * GPC + item % GPC;
       float s_, used_, mx_, finv;
       map_stats(cta, m, s_, used_, mx_, finv);
-      int o0, o1, off0, off1;
-      s_locate<Cfg>(v == 0 ? 0 : v, m, o0, off0);
-      s_locate<Cfg>(v == 0 ? HALF : N - v, m, o1, off1);
+      int off0, off1;
+      s_group_offsets<Cfg>(item % GPC, m, off0, off1);
       const float2* S = env.S(cta, cta);
       if (!(pi == 0 && v != 0)) {
 #pragma unroll
@@ -519,9 +516,8 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       ThreadRegs<Cfg>& r = env.regs(cta, tid);
       const int g = tid / TG, t = tid % TG, item = pass * NG + g;
       const int m = item / GPC, v = cta * GPC + item % GPC;
-      int o0, o1, off0, off1;
-      s_locate<Cfg>(v == 0 ? 0 : v, m, o0, off0);
-      s_locate<Cfg>(v == 0 ? HALF : N - v, m, o1, off1);
+      int off0, off1;
+      s_group_offsets<Cfg>(item % GPC, m, off0, off1);
       float2* S = env.S(cta, cta);
       inv_stage2<Cfg>(r, t, env.stg(cta) + g * STG);
       if (v == 0) {

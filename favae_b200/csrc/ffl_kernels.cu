@@ -26,7 +26,15 @@ template <class Cfg> struct DevEnv {
   __device__ __forceinline__ void sync_cta() { __syncthreads(); }
   __device__ __forceinline__ void sync_cluster() {
     if constexpr (Cfg::C == 1) __syncthreads();
-    else cg::this_cluster().sync();
+    else {
+#ifdef FAVAE_FFL_LIGHT_SYNC   // timing experiment only: CTA-scope fence + relaxed arrive (not a valid hand-over)
+      asm volatile("fence.acq_rel.cta;" ::: "memory");
+      asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+#else
+      cg::this_cluster().sync();
+#endif
+    }
   }
   // split barrier: arrive = "my reads of S are done", wait = "everybody's are" (C == 1: a CTA barrier)
   __device__ __forceinline__ void cluster_arrive() {
