@@ -97,6 +97,11 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// 16-byte cp.async (L2 only) under a predicate: no branch around the request
+__device__ __forceinline__ void cp_async16_if(unsigned smem_addr, const void* gptr, bool pred) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %2, 0; @p cp.async.cg.shared.global [%0], [%1], 16; }" ::"r"(smem_addr),
+               "l"(gptr), "r"((int)pred) : "memory");
+}
 __device__ __forceinline__ void fma4(float4& a, float k, const float4& v) {
   a.x = fmaf(k, v.x, a.x); a.y = fmaf(k, v.y, a.y); a.z = fmaf(k, v.z, a.z); a.w = fmaf(k, v.w, a.w);
 }
@@ -322,16 +327,22 @@ blur_diff_kernel(const float* __restrict__ enc, const float* __restrict__ dec, i
   constexpr int U = (FAVAE_DIFF_U > 0 && FAVAE_DIFF_U < KS) ? FAVAE_DIFF_U : KS;
   constexpr bool SHIFT = U != KS;
   constexpr int GD = 4, RS = SHIFT ? KS - 1 + U : KS, NR = TH + KS - 1;
-  __shared__ float4 ering[GD][THREADS], dring[GD][THREADS];
+  // one array for both rings: a slot of the second stream sits a constant GD * SLOT_B bytes after the
+  // first one's, and everything that does not depend on the row is computed once (the per-row request
+  // sequence was ~45 instructions of a ~190-instruction row iteration)
+  __shared__ float4 rings[2][GD][THREADS];
+  float4 (*ering)[THREADS] = rings[0];
+  float4 (*dring)[THREADS] = rings[1];
+  constexpr unsigned SLOT_B = THREADS * sizeof(float4);
+  const unsigned ring_s = (unsigned)__cvta_generic_to_shared(&rings[0][0][threadIdx.x]);
+  const float* ecol = ebase + x0;
+  const float* dcol = dbase + x0;
   auto issue_rows = [&](int r) {
-    if (live && r < NR) {
-      const int slot = r & (GD - 1);
-      const long long off = (long long)reflect_idx(y0 - P + r, h) * w + x0;
-      const unsigned de = (unsigned)__cvta_generic_to_shared(&ering[slot][threadIdx.x]);
-      const unsigned dd = (unsigned)__cvta_generic_to_shared(&dring[slot][threadIdx.x]);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(de), "l"(ebase + off) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dd), "l"(dbase + off) : "memory");
-    }
+    const bool ok = live && r < NR;
+    const unsigned sa = ring_s + (unsigned)(r & (GD - 1)) * SLOT_B;
+    const int off = reflect_idx(y0 - P + r, h) * w;          // < h * w <= 2^18
+    cp_async16_if(sa, ecol + off, ok);
+    cp_async16_if(sa + GD * SLOT_B, dcol + off, ok);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 #pragma unroll
@@ -698,21 +709,24 @@ blur_adjsig_pair_kernel(const float* __restrict__ gy, const float* __restrict__ 
   constexpr int U = (FAVAE_PAIR_U > 0 && FAVAE_PAIR_U < KS) ? FAVAE_PAIR_U : KS;
   constexpr bool SHIFT = U != KS;
   constexpr int GD = 4, RS = SHIFT ? KS - 1 + U : KS, NR = TH + KS - 1;
-  __shared__ float4 gring[GD][THREADS], xring[2][GD][THREADS];
+  // one array for the three rings (G, x_enc, x_dec): constant distances between the streams' slots, and
+  // everything that does not depend on the row computed once (see blur_diff_kernel)
+  __shared__ float4 rings[3][GD][THREADS];
+  float4 (*gring)[THREADS] = rings[0];
+  float4 (*xring)[GD][THREADS] = &rings[1];
+  constexpr unsigned SLOT_B = THREADS * sizeof(float4);
+  const unsigned ring_s = (unsigned)__cvta_generic_to_shared(&rings[0][0][threadIdx.x]);
+  const float* gcol = base + x0;
+  const float* xcol[2] = {xbase[0] + x0, xbase[1] + x0};
   auto issue_rows = [&](int r) {
-    if (live && r < NR) {
-      const int slot = r & (GD - 1);
-      const unsigned dg = (unsigned)__cvta_generic_to_shared(&gring[slot][threadIdx.x]);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dg), "l"(base + (long long)reflect_idx(y0 - P + r, h) * w + x0) : "memory");
-      const int yo = y0 + r - (KS - 1);
-      if (r >= KS - 1 && yo < h) {
-#pragma unroll
-        for (int sd = 0; sd < 2; ++sd) {
-          const unsigned dx = (unsigned)__cvta_generic_to_shared(&xring[sd][slot][threadIdx.x]);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dx), "l"(xbase[sd] + (long long)yo * w + x0) : "memory");
-        }
-      }
-    }
+    const bool ok = live && r < NR;
+    const unsigned sa = ring_s + (unsigned)(r & (GD - 1)) * SLOT_B;
+    cp_async16_if(sa, gcol + reflect_idx(y0 - P + r, h) * w, ok);
+    const int yo = y0 + r - (KS - 1);
+    const bool okx = ok && r >= KS - 1 && yo < h;
+    const int xoff = yo * w;
+    cp_async16_if(sa + GD * SLOT_B, xcol[0] + xoff, okx);
+    cp_async16_if(sa + 2 * GD * SLOT_B, xcol[1] + xoff, okx);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 #pragma unroll
