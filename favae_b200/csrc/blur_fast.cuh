@@ -73,6 +73,9 @@
 #ifndef FAVAE_DIFF_U
 #define FAVAE_DIFF_U 4   // blur-difference kernel: rows per rolled iteration (0 = KS, the renamed ring)
 #endif
+#ifndef FAVAE_ADJSIG_U
+#define FAVAE_ADJSIG_U 2   // adjoint + sigma kernel (cp.async rings): rows per rolled iteration (0 = KS)
+#endif
 #ifndef FAVAE_PAIR_U
 #define FAVAE_PAIR_U 2   // paired adjoint + sigma kernel: rows per rolled iteration (0 = KS, the renamed ring)
 #endif
@@ -474,7 +477,11 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
 // limit together with the line buffers of the narrow maps).
   constexpr int XQ = FAVAE_ADJSIG_XQ;
   constexpr int GD = FAVAE_ADJSIG_GASYNC;
-  constexpr int Q = GD ? 0 : FAVAE_ADJSIG_Q + ((XQ - (KS + FAVAE_ADJSIG_Q) % XQ) % XQ), RS = KS + Q, NR = TH + KS - 1;
+  // rows per rolled iteration with the cp.async rings: see blur_adjsig_pair_kernel (U < KS: shifted ring)
+  constexpr int U = (GD && !FAVAE_ADJSIG_FULL && FAVAE_ADJSIG_U > 0 && FAVAE_ADJSIG_U < KS) ? FAVAE_ADJSIG_U : KS;
+  constexpr bool SHIFT = U != KS;
+  constexpr int Q = GD ? 0 : FAVAE_ADJSIG_Q + ((XQ - (KS + FAVAE_ADJSIG_Q) % XQ) % XQ);
+  constexpr int RS = SHIFT ? KS - 1 + U : KS + Q, NR = TH + KS - 1;
   static_assert(RS % XQ == 0, "x prefetch ring must tile the unroll factor");
   const long long mapoff = map * (long long)h * w;
   auto load_row = [&](int r) -> float4 {
@@ -500,18 +507,19 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
   // of that iteration's output, so wait_group GD - 1 means "this iteration's rows have landed".  Each
   // thread reads back only the 16 bytes it requested itself.
   static_assert((GD & (GD - 1)) == 0, "ring depth must be a power of two");
-  __shared__ float4 gring[GD][THREADS], xring[GD][THREADS];
+  __shared__ float4 rings[2][GD][THREADS];        // one array: constant distance between the two streams' slots
+  float4 (*gring)[THREADS] = rings[0];
+  float4 (*xring)[THREADS] = rings[1];
+  constexpr unsigned SLOT_B = THREADS * sizeof(float4);
+  const unsigned ring_s = (unsigned)__cvta_generic_to_shared(&rings[0][0][threadIdx.x]);
+  const float* gcol = base + x0;
+  const float* xcol = aux ? aux + mapoff + x0 : nullptr;
   auto issue_rows = [&](int r) {
-    if (live && r < NR) {
-      const int slot = r & (GD - 1);
-      const unsigned dg = (unsigned)__cvta_generic_to_shared(&gring[slot][threadIdx.x]);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dg), "l"(base + (long long)reflect_idx(y0 - P + r, h) * w + x0) : "memory");
-      const int yo = y0 + r - (KS - 1);
-      if (r >= KS - 1 && yo < h) {
-        const unsigned dx = (unsigned)__cvta_generic_to_shared(&xring[slot][threadIdx.x]);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dx), "l"(aux + mapoff + (long long)yo * w + x0) : "memory");
-      }
-    }
+    const bool ok = live && r < NR;
+    const unsigned sa = ring_s + (unsigned)(r & (GD - 1)) * SLOT_B;
+    cp_async16_if(sa, gcol + reflect_idx(y0 - P + r, h) * w, ok);
+    const int yo = y0 + r - (KS - 1);
+    cp_async16_if(sa + GD * SLOT_B, xcol + yo * w, ok && r >= KS - 1 && yo < h);
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 #pragma unroll
@@ -539,13 +547,13 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
 #pragma unroll
   for (int q = 0; q < XQ; ++q) xq[q] = load_x(q);
 #endif
-  constexpr int STEP = FAVAE_ADJSIG_FULL ? NR : RS;
+  constexpr int STEP = FAVAE_ADJSIG_FULL ? NR : SHIFT ? U : RS;
 #pragma unroll 1
   for (int r0 = 0; r0 < NR; r0 += STEP) {
 #pragma unroll
     for (int uu = 0; uu < STEP; ++uu) {
       const int r = r0 + uu;
-      const int u = STEP == RS ? uu : uu % RS;
+      const int u = SHIFT ? KS - 1 + uu : STEP == RS ? uu : uu % RS;     // ring slot of the row that enters
       if (r >= NR) break;
 #if FAVAE_ADJSIG_GASYNC
       issue_rows(r + GD - 1);
@@ -567,7 +575,7 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
       }
       if (r < KS - 1) continue;
       const int yo = y0 + r - (KS - 1);            // output row of this iteration
-#define FAVAE_WIN(t) ring[(u + RS - (KS - 1) + (t)) % RS]
+#define FAVAE_WIN(t) ring[SHIFT ? uu + (t) : (u + RS - (KS - 1) + (t)) % RS]
       // ---- vertical pass: acc[c] = (sum_t k[t] g, sum_t k'[t] g) over the mirrored window
       float2 acc[4];
       {
@@ -638,6 +646,10 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
 #endif
         acc_sigma = fmaf(xrow.x, z[0], fmaf(xrow.y, z[1], fmaf(xrow.z, z[2], fmaf(xrow.w, z[3], acc_sigma))));
       }
+    }
+    if constexpr (SHIFT) {
+#pragma unroll
+      for (int q = 0; q < KS - 1; ++q) ring[q] = ring[q + U];
     }
   }
   acc_sigma = warp_sum(acc_sigma);
