@@ -29,6 +29,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #if defined(__CUDACC__)
 #define FAVAE_HD __host__ __device__ __forceinline__
 #else
@@ -218,6 +220,9 @@ template <class Cfg> struct ThreadRegs {
   // batch is issued before the last gradient stores of the current one
   float4 pa[Cfg::IO_V4], ta[Cfg::IO_V4], pb[Cfg::IO_V4], tb[Cfg::IO_V4];
   float sum, mx;            // running stats
+  // S addressing of the row-FFT scatter / gather without the per-element table (SFast below): entries of
+  // (owner o, column slot t) and (owner o, slot GPC - t), plus the final entries of the special elements
+  unsigned int sp[2], sm[2], sx[2];
 };
 
 struct FflParams {
@@ -268,6 +273,48 @@ template <class Cfg> FAVAE_HD void s_group_offsets(int local, int slot_map, int&
   else {
     off0 = ((slot_map * GPC + local) * 2) * Cfg::COLSTRIDE;
     off1 = off0 + Cfg::COLSTRIDE;
+  }
+}
+
+// Row-FFT scatter / gather without a table look-up per element.  Register e of lane t holds map column
+// w = t + c_e (c_e = idx_out(0, e), a multiple of R2).  With GPC a multiple of R2 the owner CTA and the column
+// slot of w are affine in t with compile-time constants per e:
+//   c_e <  N/2 :  owner c_e / GPC,              slot  t + c_e % GPC
+//   c_e >= N/2 :  group g0 - t (g0 = N - c_e):  owner (g0 - R2) / GPC,  slot  (GPC - t) + (g0 - R2) % GPC + R2
+// so six per-thread base entries (sp / sm per owner) plus an immediate reach every element.  The exception
+// is lane 0 when g0 is a multiple of GPC (column N/2, which shares group 0, and the first group of an owner):
+// those elements (two at N = 256, C = 2) keep their final entry in a register (sx).
+template <class Cfg> struct SFast {
+  static constexpr int GPC = Cfg::HALF / Cfg::C;
+#ifndef FAVAE_FFL_SFAST
+#define FAVAE_FFL_SFAST 1
+#endif
+  static constexpr bool value = FAVAE_FFL_SFAST && Cfg::S_ENTRY_MAJOR && Cfg::C == 2 && Cfg::R2 > 1 && GPC % Cfg::R2 == 0 && Cfg::R1 == Cfg::R2;
+};
+template <class Cfg, int E> struct SAddr {
+  static constexpr int N = Cfg::N, HALF = Cfg::HALF, R1 = Cfg::R1, R2 = Cfg::R2, GPC = HALF / Cfg::C;
+  static constexpr int c = R2 * (E / R2) + R1 * (E % R2);          // idx_out(0, E)
+  static constexpr bool pos = c < HALF;
+  static constexpr int g0 = N - c;
+  static constexpr bool special = !pos && (g0 % GPC == 0);
+  static constexpr int owner = pos ? c / GPC : (g0 - R2) / GPC;
+  static constexpr int delta = pos ? c % GPC : (g0 - R2) % GPC + R2;
+  static constexpr int sp_owner = (g0 == HALF) ? 0 : g0 / GPC;     // lane 0 of a special element
+  static constexpr int sp_off = GPC;
+  static constexpr int specials_before() {
+    int n = 0;
+    for (int e = 0; e < E; ++e) {
+      const int ce = R2 * (e / R2) + R1 * (e % R2);
+      if (ce >= HALF && (N - ce) % GPC == 0) ++n;
+    }
+    return n;
+  }
+  static constexpr int sidx = specials_before();
+};
+template <class Cfg, int E = 0, class F> FAVAE_HD void for_each_elem(F&& f) {
+  if constexpr (E < Cfg::R1) {
+    f(std::integral_constant<int, E>{});
+    for_each_elem<Cfg, E + 1>(f);
   }
 }
 

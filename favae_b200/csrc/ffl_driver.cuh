@@ -15,6 +15,8 @@
 //                        32-bit shared::cluster addresses, so a row-FFT lane reaches either CTA with
 //                        one table load and one add); built by ffl_init_thread
 //   env.s_put(cta, entry, at, v) / env.s_get(cta, entry, at)   S[column of entry][at] across the cluster
+//   env.s_entry_add(entry, d) / env.s_put_d<D>(...) / env.s_get_d<D>(...)   the same, D column slots further on
+//                        (a compile-time distance: an immediate on the device)
 //   env.twiddle(j, n)    e^{-2 pi i j / n}
 //   env.prefetch_l2(ptr, bytes)   hint: bring a 16-byte-aligned global range into L2
 //   env.fence_async() / env.bulk_store(gdst, ssrc, bytes) / env.bulk_commit() / env.bulk_wait_read():
@@ -37,6 +39,21 @@ FAVAE_HD void ffl_init_thread(Env& env) {
       int owner, off;
       s_locate<Cfg>(w, 0, owner, off);
       tab[w] = env.s_entry(cta, owner, off);
+    }
+    if constexpr (SFast<Cfg>::value) {
+      constexpr int GPC = SFast<Cfg>::GPC;
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        r.sp[o] = env.s_entry(cta, o, t);
+        r.sm[o] = env.s_entry(cta, o, GPC - t);
+      }
+      for_each_elem<Cfg>([&](auto ec) {
+        using A = SAddr<Cfg, decltype(ec)::value>;
+        if constexpr (A::special) {
+          static_assert(A::sidx < 2, "two special elements at most");
+          r.sx[A::sidx] = (t == 0) ? env.s_entry(cta, A::sp_owner, A::sp_off) : env.s_entry_add(r.sm[A::owner], A::delta);
+        }
+      });
     }
   });
   env.sync_cta();
@@ -230,8 +247,17 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       // map's loads and row FFTs
       if (pass == 0) env.cluster_wait();
       const int at = IS * rp + (Cfg::S_ENTRY_MAJOR ? 0 : m * (GPC * 2 * Cfg::COLSTRIDE));
+      if constexpr (SFast<Cfg>::value) {
+        for_each_elem<Cfg>([&](auto ec) {
+          constexpr int E = decltype(ec)::value;
+          using A = SAddr<Cfg, E>;
+          const unsigned int ent = A::special ? r.sx[A::sidx] : A::pos ? r.sp[A::owner] : r.sm[A::owner];
+          env.template s_put_d<(A::special ? 0 : A::delta)>(cta, ent, at, r.v[E]);
+        });
+      } else {
 #pragma unroll
-      for (int e = 0; e < R1; ++e) env.s_put(cta, tab[idx_out<Cfg>(t, e)], at, r.v[e]);
+        for (int e = 0; e < R1; ++e) env.s_put(cta, tab[idx_out<Cfg>(t, e)], at, r.v[e]);
+      }
     });
     env.sync_warp();
     env.mark(1);
@@ -555,8 +581,17 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       const int m = item / GPC, rp = cta * GPC + item % GPC;
       const unsigned int* tab = env.tab(cta);
       const int at = IS * rp + (Cfg::S_ENTRY_MAJOR ? 0 : m * (GPC * 2 * Cfg::COLSTRIDE));
+      if constexpr (SFast<Cfg>::value) {
+        for_each_elem<Cfg>([&](auto ec) {
+          constexpr int E = decltype(ec)::value;
+          using A = SAddr<Cfg, E>;
+          const unsigned int ent = A::special ? r.sx[A::sidx] : A::pos ? r.sp[A::owner] : r.sm[A::owner];
+          r.v[E] = env.template s_get_d<(A::special ? 0 : A::delta)>(cta, ent, at);
+        });
+      } else {
 #pragma unroll
-      for (int e = 0; e < R1; ++e) r.v[e] = env.s_get(cta, tab[idx_out<Cfg>(t, e)], at);
+        for (int e = 0; e < R1; ++e) r.v[e] = env.s_get(cta, tab[idx_out<Cfg>(t, e)], at);
+      }
     });
   };
   gather(0);

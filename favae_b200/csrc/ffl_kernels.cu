@@ -95,6 +95,22 @@ template <class Cfg> struct DevEnv {
       return v;
     }
   }
+  __device__ __forceinline__ unsigned int s_entry_add(unsigned int e, int d) {
+    if constexpr (Cfg::C == 1) return e + (unsigned int)d;
+    else return e + 8u * (unsigned int)d;
+  }
+  template <int D> __device__ __forceinline__ void s_put_d(int, unsigned int e, int at, float2 v) {
+    if constexpr (Cfg::C == 1) s_[e + at + D] = v;
+    else asm volatile("st.shared::cluster.v2.f32 [%0+%1], {%2, %3};" ::"r"(e + 8u * (unsigned int)at), "n"(8 * D), "f"(v.x), "f"(v.y) : "memory");
+  }
+  template <int D> __device__ __forceinline__ float2 s_get_d(int, unsigned int e, int at) {
+    if constexpr (Cfg::C == 1) return s_[e + at + D];
+    else {
+      float2 v;
+      asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v.x), "=f"(v.y) : "r"(e + 8u * (unsigned int)at), "n"(8 * D) : "memory");
+      return v;
+    }
+  }
   __device__ __forceinline__ float2* stg(int) { return stg_; }
   __device__ __forceinline__ float* fbuf(int) { return fb_; }
   __device__ __forceinline__ unsigned int* tab(int) { return tab_; }

@@ -37,6 +37,9 @@ template <class Cfg> struct HostEnv {
   unsigned int s_entry(int, int owner, int off) { return ((unsigned int)owner << 24) | (unsigned int)off; }
   void s_put(int cta, unsigned int e, int at, float2 v) { S(cta, (int)(e >> 24))[(int)(e & 0xFFFFFFu) + at] = v; }
   float2 s_get(int cta, unsigned int e, int at) { return S(cta, (int)(e >> 24))[(int)(e & 0xFFFFFFu) + at]; }
+  unsigned int s_entry_add(unsigned int e, int d) { return e + (unsigned int)d; }
+  template <int D> void s_put_d(int cta, unsigned int e, int at, float2 v) { s_put(cta, e, at + D, v); }
+  template <int D> float2 s_get_d(int cta, unsigned int e, int at) { return s_get(cta, e, at + D); }
   void prefetch_l2(const void*, size_t) {}
   void fence_async() {}
   void bulk_store(void* gdst, const void* ssrc, size_t bytes) { std::memcpy(gdst, ssrc, bytes); }
