@@ -215,22 +215,45 @@ class _CodebookBase(nn.Module):
         self._flush()
         self.__dict__['_prep'] = None
 
-    def _defers_ema(self, t):
-        """True when the statistics all-reduce of this call runs on the side stream and the EMA waits for
-        the next touch of the codebook."""
+    def _distributed(self):
         import torch.distributed as dist
-        return bool(self.use_ddp and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-                    and t.is_cuda and self.threshold_ema_dead_code == 0)
+        return bool(self.use_ddp and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
 
     def _ema_on_side_stream(self, t):
+        """True when the tail of a training call -- the statistics all-reduce of a data-parallel run and the
+        EMA update -- runs on the side stream (cosine codebook without dead-code expiry; FAVAE_EMA_STREAM=0
+        disables it)."""
         return bool(t.is_cuda and self.threshold_ema_dead_code == 0 and self.cosine
                     and os.environ.get('FAVAE_EMA_STREAM', '1') not in ('', '0'))
 
+    def _defers_ema(self, t):
+        """True when the statistics all-reduce of this call runs on the side stream and the EMA itself waits
+        for the next touch of the codebook (data-parallel runs of the codebooks the side-stream update does
+        not cover)."""
+        return bool(self._distributed() and t.is_cuda and self.threshold_ema_dead_code == 0
+                    and not self._ema_on_side_stream(t))
+
     def _after_stats(self, en, eh, stats):
         """Statistics of this call are ready on the current stream: all-reduce + EMA."""
+        if self._ema_on_side_stream(stats):
+            # Nothing of this call reads the updated codebook (its outputs use the pre-update one, reference
+            # :415 before :421-438), so the whole tail leaves the caller's stream: ONE all-reduce of
+            # [bins | embed_sum] in a data-parallel run (reference: two blocking ones, :419/:427 and :291/:295)
+            # and the EMA update run on the side stream, next to whatever the caller does after the quantizer
+            # (decoder, spectrum losses, backward); the next touch of the codebook waits for the event.
+            side = _side_stream(stats.device)
+            side.wait_stream(torch.cuda.current_stream(stats.device))
+            with torch.cuda.stream(side):
+                if self._distributed():
+                    _dist.all_reduce_stats(stats)
+                elif self.use_ddp:
+                    _dist.all_reduce_stats(stats)      # raises like the reference without a process group
+                self._ema_update(en, eh, stats)
+                done = torch.cuda.Event()
+                done.record(side)
+            self.__dict__['_pending'] = (stats, None, None, done)
+            return
         if self._defers_ema(stats):
-            # one all-reduce of [bins | embed_sum] (reference: two blocking ones, :419/:427 and :291/:295),
-            # on a side stream; the EMA waits for it at the next touch of the codebook (_flush)
             side = _side_stream(stats.device)
             side.wait_stream(torch.cuda.current_stream(stats.device))
             with torch.cuda.stream(side):
@@ -241,18 +264,6 @@ class _CodebookBase(nn.Module):
             return
         if self.use_ddp:
             _dist.all_reduce_stats(stats)      # raises like the reference without a process group
-        if self._ema_on_side_stream(stats):
-            # Single process: nothing of this call reads the updated codebook (its outputs use the
-            # pre-update one, reference :415 before :421-438), so the update runs on the side stream next to
-            # whatever the caller does after the quantizer; the next touch of the codebook waits for it.
-            side = _side_stream(stats.device)
-            side.wait_stream(torch.cuda.current_stream(stats.device))
-            with torch.cuda.stream(side):
-                self._ema_update(en, eh, stats)
-                done = torch.cuda.Event()
-                done.record(side)
-            self.__dict__['_pending'] = (stats, None, None, done)
-            return
         self._ema_update(en, eh, stats)
 
     # -- kernels --------------------------------------------------------------------------
@@ -411,10 +422,11 @@ class _CodebookBase(nn.Module):
             raise RuntimeError(f'favae_b200: latents on {dev} but the codebook is on {embed.device}')
         idx, en, eh = self._search_rows(xn, xh, None, n)
 
-        # When the EMA is deferred (data-parallel run: _after_stats only launches the all-reduce on the side
-        # stream), the statistics come first so that the collective also overlaps the gather of this call;
-        # otherwise the EMA would overwrite the codebook the gather still has to read (reference :415
-        # gathers before :421-438 update), so the order stays gather -> statistics -> EMA.
+        # When only the all-reduce leaves the caller's stream and the EMA is deferred to the next touch
+        # (_defers_ema), the statistics come first so that the collective also overlaps the gather of this
+        # call; otherwise the EMA (inline, or on the side stream right behind the collective) would overwrite
+        # the codebook the gather still has to read (reference :415 gathers before :421-438 update), so the
+        # order stays gather -> statistics -> [all-reduce ->] EMA.
         early = self.training and self._defers_ema(x)
         if early:
             stats = self._code_stats(xn, idx, n, self._buf('stats', (k * (d + 1),), torch.float32, dev))
