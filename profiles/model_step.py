@@ -50,9 +50,11 @@ def run(fcm, vl, ffl, dsl, batch, steps, warmup, label):
         opt_d.step()
         return loss.detach()
 
-    for _ in range(warmup):
+    first = [float(step()) for _ in range(min(warmup, 3))]          # same weights / input in both variants
+    for _ in range(warmup - len(first)):
         step()
     torch.cuda.synchronize()
+    print(f'{label:<46} loss of the first steps: ' + ' '.join(f'{v:.6f}' for v in first), flush=True)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     a.record()

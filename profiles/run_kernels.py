@@ -43,10 +43,15 @@ def main():
 
     shape = (B, 128, 256, 256)
     E = B * 128 * 256 * 256
-    if want('ffl') or want('blur_fwd') or want('blur_bwd') or want('blur_diff') or want('blur_pair'):
+    if want('ffl') or want('ffl_diff') or want('blur_fwd') or want('blur_bwd') or want('blur_diff') or want('blur_pair'):
         p = torch.randn(shape, device=dev); t = torch.randn(shape, device=dev)
         gp = torch.empty_like(p); gt = torch.empty_like(p)
         sig = torch.tensor(3.0, device=dev)
+    if want('ffl_diff'):
+        ml = torch.empty(B * 128, device=dev)
+        ms = timed(lambda: _lib.call('favae_ffl_forward', p.data_ptr(), None, B * 128, 256, 256, 1.0, 0,
+                                     1e-3, ml.data_ptr(), gp.data_ptr(), None, None, None, st()), it)
+        print(f'ffl_256 d -> G          {ms:8.3f} ms  {8 * E / ms / 1e6:8.1f} GB/s algorithmic (8 B/elem)')
     if want('ffl'):
         ml = torch.empty(B * 128, device=dev)
         ms = timed(lambda: _lib.call('favae_ffl_forward', p.data_ptr(), t.data_ptr(), B * 128, 256, 256, 1.0, 0,
