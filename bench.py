@@ -667,17 +667,17 @@ def main():
         os._exit(1 if failed else 0)
 
 
-# ncu --set full captures of this round (profiles/ncu_r2_summary.md): dram__bytes_read + write per element
+# ncu --set full captures of this round (profiles/ncu_r2_summary.md, last section): dram__bytes_read + write per element
 NCU_TRAFFIC = {
     'blur_backward': (12.00, 'ncu --set full, blur_adjsig_kernel<9,64>: 561.9 MB read + 242.9 MB written for 1024 maps '
                              'of 256^2 = 12.00 B/element (profiles/ncu_r2_blur_bwd_raw.csv)'),
-    'blur_diff': (12.27, 'ncu --set full, blur_diff_kernel<9,64>: 586.5 MB read + 236.9 MB written for 1024 maps of '
-                         '256^2 = 12.27 B/element (profiles/ncu_r2_blur_diff_raw.csv)'),
-    'ffl_diff': (7.12, 'ncu --set full, ffl_kernel<256> single-input form: 268.5 MB read + 209.1 MB written for 1024 maps '
-                       'of 256^2 = 7.12 B/element, part of the last gradient stores still in L2 when the kernel ends '
-                       '(profiles/ncu_r2_ffldiff_raw.csv)'),
-    'blur_pair': (19.67, 'ncu --set full, blur_adjsig_pair_kernel<9,128> (2-row body): 813.7 MB read + 506.5 MB written for '
-                         '1024 maps of 256^2 = 19.67 B/element (profiles/ncu_r2b_blur_pair_raw.csv)'),
+    'blur_diff': (12.30, 'ncu --set full, blur_diff_kernel<9,64>: 586.5 MB read + 239.2 MB written for 1024 maps of '
+                         '256^2 = 12.30 B/element (profiles/ncu_r2b_diff_raw.csv)'),
+    'ffl_diff': (7.29, 'ncu --set full, ffl_kernel<256> single-input form: 268.5 MB read + 220.6 MB written for 1024 maps '
+                       'of 256^2 = 7.29 B/element, part of the last gradient rows still in L2 when the kernel ends '
+                       '(profiles/ncu_r2b_ffldiff_raw.csv)'),
+    'blur_pair': (19.61, 'ncu --set full, blur_adjsig_pair_kernel<9,128>: 813.7 MB read + 502.5 MB written for 1024 maps '
+                         'of 256^2 = 19.61 B/element (profiles/ncu_r2b_pair_raw.csv)'),
     'ffl2': (15.48, 'ncu --set full, ffl_kernel<256> two-input form: 15.48 B/element (profiles/ncu_r1_summary.md)')}
 
 
