@@ -503,6 +503,28 @@ def _ffl_cufft(p, t, lw):
     return (w * m2 * mult).sum() * (lw / p.numel())
 
 
+@pytest.mark.parametrize('maps,side', [(1, 256), (3, 256), (75, 256), (149, 256), (300, 256), (19, 512)])
+def test_single_input_form_in_place_bulk_rows(maps, side):
+    """favae_ffl_forward(d, NULL) writing G over d (the fused DSL level's call) against the cuFFT restatement,
+    with map counts below, at and above the number of resident clusters: gradient rows leave shared memory
+    through bulk async copies from the FFT staging area, which the next map's first exchange reuses."""
+    from favae_b200 import _lib
+    g = torch.Generator(device='cuda').manual_seed(maps + side)
+    d = torch.randn(maps, 1, side, side, device='cuda', generator=g)
+    ref_in = d.clone().requires_grad_(True)
+    lw = 0.01
+    ref = _ffl_cufft(ref_in, torch.zeros_like(ref_in), lw)
+    ref.backward()
+    ml = torch.empty(maps, device='cuda')
+    gscale = 2.0 * lw / d.numel()
+    with _lib.on_device_of(d):
+        _lib.call('favae_ffl_forward', _lib.ptr(d), None, maps, side, side, 1.0, 0, gscale, _lib.ptr(ml),
+                  _lib.ptr(d), None, None, None, _lib.stream())
+    loss = float(ml.double().sum()) * lw / d.numel()
+    assert loss == pytest.approx(float(ref), rel=RTOL)
+    assert float((d - ref_in.grad).abs().max()) <= RTOL * float(ref_in.grad.abs().max())
+
+
 def test_full_size_level0_against_cufft_and_conv2d():
     """Batch 32 level-0 size (4096 maps of 256^2 per tensor): the spectrum loss and both gradients
     against a cuFFT restatement, the blur forward / adjoint / sigma gradient against F.conv2d autograd,

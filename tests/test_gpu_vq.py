@@ -480,3 +480,33 @@ def test_tensors_on_a_non_current_device(monkeypatch):
     assert float(f0) == float(f1)
     with pytest.raises(RuntimeError):
         FocalFrequencyLoss()(p.to('cuda:0'), t.to('cuda:1'))
+
+
+@pytest.mark.gpu
+def test_ema_on_the_side_stream_matches_the_inline_update(monkeypatch):
+    """The training call leaves its tail (statistics -> EMA) on a side stream; FAVAE_EMA_STREAM=0 keeps it on the
+    caller's stream.  Same codebook, indices and loss either way, bit for bit, over several steps -- and the
+    pending update is applied before anybody can look at the codebook."""
+    from favae_b200 import VectorQuantize
+    monkeypatch.setenv('FAVAE_VQ_DETERMINISTIC', '1')                 # ordered statistics: bit-comparable runs
+    torch.manual_seed(3)
+    a = VectorQuantize(dim=256, codebook_size=1024, accept_image_fmap=True, use_cosine_sim=True).cuda().train()
+    b = VectorQuantize(dim=256, codebook_size=1024, accept_image_fmap=True, use_cosine_sim=True).cuda().train()
+    b.load_state_dict(a.state_dict())
+    g = torch.Generator(device='cuda').manual_seed(4)
+    for step in range(3):
+        x = torch.randn(4, 256, 16, 16, device='cuda', generator=g)
+        monkeypatch.setenv('FAVAE_EMA_STREAM', '1')
+        qa, ia, la = a(x)
+        assert a._codebook.__dict__.get('_pending') is not None        # update in flight on the side stream
+        monkeypatch.setenv('FAVAE_EMA_STREAM', '0')
+        qb, ib, lb = b(x)
+        assert b._codebook.__dict__.get('_pending') is None
+        assert torch.equal(ia, ib) and torch.equal(qa, qb) and torch.equal(la, lb)
+        assert torch.equal(a._codebook.embed, b._codebook.embed)       # the access waits for the side stream
+        assert a._codebook.__dict__.get('_pending') is None
+        assert torch.equal(a._codebook.cluster_size, b._codebook.cluster_size)
+    with torch.no_grad():
+        a.eval(); b.eval()
+        x = torch.randn(2, 256, 16, 16, device='cuda', generator=g)
+        assert torch.equal(a(x)[1], b(x)[1])
