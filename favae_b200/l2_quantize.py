@@ -100,6 +100,7 @@ class _QuantizeFunction(torch.autograd.Function):
         out, idx, loss_sum = codebook._search_and_gather(x, n, hw, straight_through, want_loss)
         ctx.save_for_backward(x, out)
         ctx.mark_non_differentiable(idx)
+        ctx.codebook = codebook
         return out, idx, loss_sum
 
     @staticmethod
@@ -111,6 +112,11 @@ class _QuantizeFunction(torch.autograd.Function):
         with _lib.on_device_of(x, g_out, g_loss):
             _lib.call('favae_vq_backward', _lib.ptr(x), _lib.ptr(out), _lib.ptr(g_out), _lib.ptr(g_loss),
                       x.numel(), 2.0, _lib.ptr(gx), _lib.stream())
+            # The side-stream tail of the forward call (all-reduce + EMA) finished long ago: joining it here
+            # costs nothing and orders everything the caller does after backward -- optimizer step, DDP's
+            # buffer broadcast of the next forward, which reads the buffers without going through the module
+            # attributes -- behind the codebook update.
+            ctx.codebook._flush()
         return gx, None, None, None, None
 
 
