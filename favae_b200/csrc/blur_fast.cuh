@@ -71,13 +71,13 @@
 #define FAVAE_ADJSIG_TH 64   // adjoint + sigma kernel: strip height on maps of >= 128 rows
 #endif
 #ifndef FAVAE_DIFF_U
-#define FAVAE_DIFF_U 4   // blur-difference kernel: rows per rolled iteration (0 = KS, the renamed ring)
+#define FAVAE_DIFF_U 0   // blur-difference kernel: rows per rolled iteration (0 = KS, the renamed ring: its 9-row body still fits)
 #endif
 #ifndef FAVAE_ADJSIG_U
-#define FAVAE_ADJSIG_U 2   // adjoint + sigma kernel (cp.async rings): rows per rolled iteration (0 = KS)
+#define FAVAE_ADJSIG_U 4   // adjoint + sigma kernel (cp.async rings): rows per rolled iteration (0 = KS); even values keep the line / ring parities static
 #endif
 #ifndef FAVAE_PAIR_U
-#define FAVAE_PAIR_U 2   // paired adjoint + sigma kernel: rows per rolled iteration (0 = KS, the renamed ring)
+#define FAVAE_PAIR_U 4   // paired adjoint + sigma kernel: rows per rolled iteration (0 = KS, the renamed ring); measured 1: 1.17, 2: 1.05, 3: 1.08, 4: 1.01, 5: 1.09, 6: 1.02 ms
 #endif
 #ifndef FAVAE_PAIR_TH
 #define FAVAE_PAIR_TH 128   // paired adjoint + sigma kernel: strip height on maps of >= 256 rows
