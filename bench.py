@@ -676,8 +676,8 @@ NCU_TRAFFIC = {
     'ffl_diff': (7.29, 'ncu --set full, ffl_kernel<256> single-input form: 268.5 MB read + 220.6 MB written for 1024 maps '
                        'of 256^2 = 7.29 B/element, part of the last gradient rows still in L2 when the kernel ends '
                        '(profiles/ncu_r2b_ffldiff_raw.csv)'),
-    'blur_pair': (19.61, 'ncu --set full, blur_adjsig_pair_kernel<9,128>: 813.7 MB read + 502.5 MB written for 1024 maps '
-                         'of 256^2 = 19.61 B/element (profiles/ncu_r2b_pair_raw.csv)'),
+    'blur_pair': (19.64, 'ncu --set full, blur_adjsig_pair_kernel<9,128>: 813.7 MB read + 504.0 MB written for 1024 maps '
+                         'of 256^2 = 19.64 B/element (profiles/ncu_r2b_pair_raw.csv)'),
     'ffl2': (15.48, 'ncu --set full, ffl_kernel<256> two-input form: 15.48 B/element (profiles/ncu_r1_summary.md)')}
 
 
