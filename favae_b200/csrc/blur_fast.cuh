@@ -669,11 +669,14 @@ blur_adjsig_kernel(const float* __restrict__ src, const float* __restrict__ aux,
 // launches); here the G rows, the window, the E row scaling and the mirrored pre-adds of the vertical
 // pass are shared and only the tap-dependent work is done per side: 20 B/element and ~19 % fewer
 // instructions than two launches.  Same structure otherwise (cp.async rings for G and the two x streams,
-// one barrier per row for both sides' shared lines, taps in uniform registers).  ncu (1024 maps of
-// 256^2): 208.5 M warp instructions against 2 x 120.6 M, 19.9 B/element, issue active 59 %, but
-// `no_instruction` 1.5 cycles per issue -- the 9-row body is 4.4 k instructions.  Rolling the two side
-// loops (taps re-read from shared memory, own columns re-read from the line) cures the fetch stalls and
-// costs more than it saves: 3.3 k static / 238.6 M executed instructions, 1.32 ms against 1.23 ms.
+// one barrier per row for both sides' shared lines, taps in uniform registers).  First version (KS rows
+// unrolled over a renamed ring), ncu at 1024 maps of 256^2: 208.5 M warp instructions against 2 x 120.6 M,
+// 19.9 B/element, issue active 59 %, but `no_instruction` 1.5 cycles per issue -- the 9-row body was 4.4 k
+// instructions (70 KB).  Rolling the two side loops (taps re-read from shared memory, own columns re-read
+// from the line) cured the fetch stalls and cost more than it saved: 3.3 k static / 238.6 M executed
+// instructions, 1.32 ms against 1.23 ms.  What did work: U rows per rolled trip over a ring that is shifted
+// with register moves (below), 128-row strips and predicated row requests: 186.6 M instructions, no fetch
+// stalls, 1.01 ms = 0.81 of HBM peak (profiles/ncu_r2_summary.md, last section).
 template <int KS, int TH>
 __global__ void __launch_bounds__(THREADS, KS <= 9 ? FAVAE_ADJSIG_MINB : KS == 11 ? 3 : 2)
 blur_adjsig_pair_kernel(const float* __restrict__ gy, const float* __restrict__ x_enc, const float* __restrict__ x_dec,
