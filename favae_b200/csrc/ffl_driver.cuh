@@ -140,6 +140,9 @@ template <class Cfg, bool DIFF> struct FflPipe {
   static constexpr bool value =
       !FflDirect<Cfg, DIFF>::load && (Cfg::PIPELINE_LOADS || (DIFF && Cfg::C == 2 && FAVAE_FFL_DIFF_PIPE));
 };
+#ifndef FAVAE_FFL_MERGE_STAGE1
+#define FAVAE_FFL_MERGE_STAGE1 1
+#endif
 template <class Cfg, bool FAST = false, bool DIFF = false, class Env>
 FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long long next_batch = -1) {
   constexpr bool PIPE = FflPipe<Cfg, DIFF>::value;
@@ -155,6 +158,11 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
   const float inv_nn = 1.0f / (float)(N * N);
   const float inv_n = 1.0f / (float)N;
   const long long map0 = batch * MPC;
+  // f(A) of the packed columns (P3 / P4): the lean path has f = A = sqrt(A^2), no run-time alpha / log cases
+  auto spec_f = [&](float a2) -> float {
+    if constexpr (FAST) return favae_fast_sqrt(a2);
+    else return spectrum_f(a2, p.alpha, p.log_matrix);
+  };
 
   env.for_threads([&](int cta, int tid) {
     ThreadRegs<Cfg>& r = env.regs(cta, tid);
@@ -313,9 +321,11 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
           r.v[e] = make_float2(zv.x, zw.x);
           r.v[e + R1 / 2] = make_float2(zv.y, zw.y);
         }
+#if !FAVAE_FFL_MERGE_STAGE1
         // (stage 1 sits inside both branches: they merge after the values have gone to staging,
         // not through two dozen register copies)
         fwd_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
+#endif
       } else {                                           // separate the two packed real rows
 #pragma unroll
         for (int e = 0; e < R1 / 2; ++e) {
@@ -325,8 +335,16 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
           r.v[e] = pk_fma(zw, make_float2(0.5f, -0.5f), pk_mul(zv, make_float2(0.5f, 0.5f)));
           r.v[e + R1 / 2] = pk_fma(pk_swap(zv), make_float2(0.5f, -0.5f), pk_mul(pk_swap(zw), make_float2(0.5f, 0.5f)));
         }
+#if !FAVAE_FFL_MERGE_STAGE1
         fwd_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
+#endif
       }
+#if FAVAE_FFL_MERGE_STAGE1
+      // one copy of stage 1 behind the branch: the warp that holds column group 0 next to an ordinary group
+      // would otherwise run the ~200 instructions of stage 1 twice, once per side of the branch, and every
+      // other warp of the cluster waits for it at the statistics barrier
+      fwd_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
+#endif
     });
     env.sync_warp();
     env.for_threads([&](int cta, int tid) {
@@ -398,8 +416,8 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
         const float mult = (u == 0 || u == HALF) ? 1.0f : 2.0f;
         const float a0 = (d0.x * d0.x + d0.y * d0.y) * inv_nn;
         const float an = (dn.x * dn.x + dn.y * dn.y) * inv_nn;
-        const float f0 = spectrum_f(a0, p.alpha, p.log_matrix);
-        const float fn = spectrum_f(an, p.alpha, p.log_matrix);
+        const float f0 = spec_f(a0);
+        const float fn = spec_f(an);
         r.sum += mult * (f0 * a0 + fn * an);
         r.mx = fmaxf(r.mx, fmaxf(f0, fn));
       }
@@ -494,8 +512,8 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       const float2 dn = make_float2(0.5f * (a.y + b.y), 0.5f * (b.x - a.x));
       const float a0 = (d0.x * d0.x + d0.y * d0.y) * inv_nn;
       const float an = (dn.x * dn.x + dn.y * dn.y) * inv_nn;
-      const float w0 = spectrum_w(spectrum_f(a0, p.alpha, p.log_matrix), finv) * p.grad_scale;
-      const float wn = spectrum_w(spectrum_f(an, p.alpha, p.log_matrix), finv) * p.grad_scale;
+      const float w0 = spectrum_w(spec_f(a0), finv) * p.grad_scale;
+      const float wn = spectrum_w(spec_f(an), finv) * p.grad_scale;
       S[ia] = make_float2(w0 * d0.x - wn * dn.y, w0 * d0.y + wn * dn.x);
       if (ib != ia) S[ib] = make_float2(w0 * d0.x + wn * dn.y, wn * dn.x - w0 * d0.y);
     }
