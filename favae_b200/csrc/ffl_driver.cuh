@@ -140,8 +140,13 @@ template <class Cfg, bool DIFF> struct FflPipe {
   static constexpr bool value =
       !FflDirect<Cfg, DIFF>::load && (Cfg::PIPELINE_LOADS || (DIFF && Cfg::C == 2 && FAVAE_FFL_DIFF_PIPE));
 };
+// Column group 0 (the packed real columns 0 and N/2) shares a warp with an ordinary group.  0: a branch with
+// stage 1 duplicated on both sides (that warp runs stage 1 twice); 1: one stage 1 behind the branch (the
+// compiler reconciles the two register layouts with ~55 moves on the common path); 2: branch-free, the
+// general separation for every lane and the packed columns selected over it (32 selects per pass).
+// Measured, 4096 maps of 256^2, single-input form: 0.967 / 0.974 / 0.958 ms.
 #ifndef FAVAE_FFL_MERGE_STAGE1
-#define FAVAE_FFL_MERGE_STAGE1 1
+#define FAVAE_FFL_MERGE_STAGE1 2
 #endif
 template <class Cfg, bool FAST = false, bool DIFF = false, class Env>
 FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long long next_batch = -1) {
@@ -313,6 +318,23 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
       int off0, off1;
       s_group_offsets<Cfg>(item % GPC, m, off0, off1);
       const float2* S = env.S(cta, cta);
+#if FAVAE_FFL_MERGE_STAGE1 == 2
+      // branch-free: the general separation for every lane, the packed real columns of group 0 selected over it
+      {
+        const bool g0 = v == 0;
+#pragma unroll
+        for (int e = 0; e < R1 / 2; ++e) {
+          const int rr = idx_in<Cfg>(t, e);
+          const float2 zv = S[off0 + IS * rr], zw = S[off1 + IS * rr];
+          const float2 a = pk_fma(zw, make_float2(0.5f, -0.5f), pk_mul(zv, make_float2(0.5f, 0.5f)));
+          const float2 b = pk_fma(pk_swap(zv), make_float2(0.5f, -0.5f), pk_mul(pk_swap(zw), make_float2(0.5f, 0.5f)));
+          r.v[e] = g0 ? make_float2(zv.x, zw.x) : a;
+          r.v[e + R1 / 2] = g0 ? make_float2(zv.y, zw.y) : b;
+        }
+        fwd_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
+      }
+      if (false)
+#endif
       if (v == 0) {                                      // packed real columns 0 and N/2
 #pragma unroll
         for (int e = 0; e < R1 / 2; ++e) {
@@ -321,7 +343,7 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
           r.v[e] = make_float2(zv.x, zw.x);
           r.v[e + R1 / 2] = make_float2(zv.y, zw.y);
         }
-#if !FAVAE_FFL_MERGE_STAGE1
+#if FAVAE_FFL_MERGE_STAGE1 == 0
         // (stage 1 sits inside both branches: they merge after the values have gone to staging,
         // not through two dozen register copies)
         fwd_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
@@ -335,11 +357,11 @@ FAVAE_HD void ffl_map_batch(Env& env, const FflParams& p, long long batch, long 
           r.v[e] = pk_fma(zw, make_float2(0.5f, -0.5f), pk_mul(zv, make_float2(0.5f, 0.5f)));
           r.v[e + R1 / 2] = pk_fma(pk_swap(zv), make_float2(0.5f, -0.5f), pk_mul(pk_swap(zw), make_float2(0.5f, 0.5f)));
         }
-#if !FAVAE_FFL_MERGE_STAGE1
+#if FAVAE_FFL_MERGE_STAGE1 == 0
         fwd_stage1<Cfg>(r, t, env.stg(cta) + g * STG);
 #endif
       }
-#if FAVAE_FFL_MERGE_STAGE1
+#if FAVAE_FFL_MERGE_STAGE1 == 1
       // one copy of stage 1 behind the branch: the warp that holds column group 0 next to an ordinary group
       // would otherwise run the ~200 instructions of stage 1 twice, once per side of the branch, and every
       // other warp of the cluster waits for it at the statistics barrier
