@@ -673,8 +673,8 @@ NCU_TRAFFIC = {
                              'of 256^2 = 12.00 B/element (profiles/ncu_r2_blur_bwd_raw.csv)'),
     'blur_diff': (12.30, 'ncu --set full, blur_diff_kernel<9,64>: 586.5 MB read + 239.2 MB written for 1024 maps of '
                          '256^2 = 12.30 B/element (profiles/ncu_r2b_diff_raw.csv)'),
-    'ffl_diff': (7.29, 'ncu --set full, ffl_kernel<256> single-input form: 268.5 MB read + 220.6 MB written for 1024 maps '
-                       'of 256^2 = 7.29 B/element, part of the last gradient rows still in L2 when the kernel ends '
+    'ffl_diff': (7.30, 'ncu --set full, ffl_kernel<256> single-input form: 268.7 MB read + 221.4 MB written for 1024 maps '
+                       'of 256^2 = 7.30 B/element, part of the last gradient rows still in L2 when the kernel ends '
                        '(profiles/ncu_r2b_ffldiff_raw.csv)'),
     'blur_pair': (19.64, 'ncu --set full, blur_adjsig_pair_kernel<9,128>: 813.7 MB read + 504.0 MB written for 1024 maps '
                          'of 256^2 = 19.64 B/element (profiles/ncu_r2b_pair_raw.csv)'),
