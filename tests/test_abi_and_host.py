@@ -162,3 +162,44 @@ def test_sigma_element_is_select_with_one_autograd_node():
         assert sigma_element(s, 2).grad_fn is None                  # (like s[2] under no_grad)
     assert sigma_element(s, 2).grad_fn is not None
     assert float(sigma_element([1.0, 2.0], 1)) == 2.0               # anything else: plain indexing
+
+
+def test_shipped_library_holds_the_blackwell_instructions():
+    """The built library is sm_100a code with the instructions the design rests on (cuobjdump -sass; no GPU
+    needed): tcgen05 MMA / TMEM load / TMA tensor loads in the search, bulk async copies and packed fp32x2
+    arithmetic in the spectrum loss, cp.async and packed arithmetic in the blur kernels."""
+    import shutil
+    import subprocess
+    from favae_b200 import _build
+    tool = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(tool):
+        pytest.skip('cuobjdump not available')
+    lib = _build.build(verbose=False)
+    sass = subprocess.run([tool, '-sass', lib], capture_output=True, text=True, check=True).stdout
+    assert 'sm_100a' in sass
+    kernels = {}
+    name = None
+    for line in sass.splitlines():
+        if 'Function :' in line:
+            name = line.split('Function :')[1].strip()
+            kernels[name] = set()
+        elif name and '/*' in line:
+            parts = line.split('*/', 1)
+            if len(parts) == 2 and parts[1].strip():
+                tok = parts[1].split()
+                op = tok[1] if tok[0].startswith('@') and len(tok) > 1 else tok[0]
+                kernels[name].add(op.split('.')[0])
+
+    def ops(substr):
+        found = set()
+        for k, v in kernels.items():
+            if substr in k:
+                found |= v
+        assert found, substr
+        return found
+    search = ops('vq_search_tc_kernel')
+    assert {'UTCHMMA', 'LDTM', 'UTMALDG'} <= search, sorted(search)
+    ffl = ops('ffl_kernelINS_6FflCfgILi256ELi2ELi1ELi512EEELb1ELb1')
+    assert {'FADD2', 'FFMA2', 'UBLKCP'} <= ffl, sorted(ffl)
+    pair = ops('blur_adjsig_pair_kernel')
+    assert {'LDGSTS', 'FFMA2'} <= pair, sorted(pair)
