@@ -184,7 +184,7 @@ def sigma_element(sigmas, i):
         # the stale views go first: they keep the vector's AccumulateGrad node (and its stream) alive, and the
         # new views must not be wired to it
         _UNBOUND.pop(id(sigmas), None)
-        cached = None
+        cached = None                            # (the local reference to the stale views as well)
         cached = _UNBOUND[id(sigmas)] = (sigmas, key, sigmas.unbind(0))
     return cached[2][i]
 

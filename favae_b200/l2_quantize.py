@@ -250,10 +250,8 @@ class _CodebookBase(nn.Module):
             side = _side_stream(stats.device)
             side.wait_stream(torch.cuda.current_stream(stats.device))
             with torch.cuda.stream(side):
-                if self._distributed():
-                    _dist.all_reduce_stats(stats)
-                elif self.use_ddp:
-                    _dist.all_reduce_stats(stats)      # raises like the reference without a process group
+                if self.use_ddp:
+                    _dist.all_reduce_stats(stats)      # (raises like the reference without a process group)
                 self._ema_update(en, eh, stats)
                 done = torch.cuda.Event()
                 done.record(side)
